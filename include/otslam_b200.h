@@ -1,0 +1,137 @@
+/* otslam_b200.h -- C ABI of the B200-native RGB-D reconstruction hot path.
+ *
+ * The reference (TakiRyo/object-triggered-3D-SLAM) has no FFI of its own for this path: its four
+ * scripts reach the arithmetic through the `open3d` Python package.  Each entry point below names
+ * the reference call site (file:line under /root/reference) whose work it replaces; the binding a
+ * maintainer adds is the ctypes shim shown in INTEGRATION.md (shipped as
+ * object-triggered-3d-slam_b200/_lib.py + o3d_compat/).
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 (OTSLAM_OK) or a negative
+ * status, with a message available from otslam_last_error() (thread-local).  Matrices are 4x4
+ * row-major FP64.  Unless a function says "device", pointers are HOST pointers and the call is
+ * synchronous (results visible on return).  There is no CPU fallback: every call fails with
+ * OTSLAM_ERR_CUDA when no sm_100 GPU is usable.
+ */
+#ifndef OTSLAM_B200_H
+#define OTSLAM_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OTSLAM_OK 0
+#define OTSLAM_ERR_INVALID (-1)   /* bad argument */
+#define OTSLAM_ERR_FORMAT (-2)    /* "[ScalableTSDFVolume::Integrate] Unsupported image format." */
+#define OTSLAM_ERR_CUDA (-3)      /* CUDA runtime / no device */
+#define OTSLAM_ERR_NOMEM (-4)     /* device memory exhausted */
+#define OTSLAM_ERR_OVERFLOW (-5)  /* per-voxel frame-count limit (65535) or key range exceeded */
+
+#define OTSLAM_MEM_HOST 0
+#define OTSLAM_MEM_DEVICE 1
+
+#define OTSLAM_COLOR_NONE 0       /* TSDFVolumeColorType.NoColor */
+#define OTSLAM_COLOR_RGB8 1       /* TSDFVolumeColorType.RGB8 (reconstruct_rgbd.py:82) */
+
+typedef struct otslam_volume otslam_volume;
+
+/* Spatial slab sharding of the block grid across the GPUs of one box: block key k on
+ * `axis` is owned by rank (floor(k / thickness) mod n_ranks); a rank also keeps the +1 neighbour
+ * blocks of the blocks it owns (halo) so that extraction is local. n_ranks == 1: keep everything. */
+typedef struct {
+    int32_t axis, thickness, n_ranks, rank;
+} otslam_slab_spec;
+
+const char* otslam_last_error(void);
+int otslam_version(void);
+/* number of CUDA kernels this library has launched in this process (bench.py "gpu_launches") */
+int64_t otslam_launch_count(void);
+
+/* ---- volume life cycle: o3d.pipelines.integration.ScalableTSDFVolume(voxel_length, sdf_trunc,
+ *      color_type) (3d_model/reconstruct_rgbd.py:79-83); volume_unit_resolution = 16,
+ *      depth_sampling_stride = 4 as in Open3D. `slab` may be NULL. */
+int otslam_volume_create(double voxel_length, double sdf_trunc, int color_type, int device,
+                         const otslam_slab_spec* slab, otslam_volume** out);
+int otslam_volume_destroy(otslam_volume* v);
+int otslam_volume_reset(otslam_volume* v);                       /* ScalableTSDFVolume.reset() */
+/* run this volume's kernels on a caller-owned cudaStream_t (e.g. torch's current stream) */
+int otslam_volume_set_stream(otslam_volume* v, void* cuda_stream);
+/* frames fused per block residency in integrate_batch (1..32, default 32) */
+int otslam_volume_set_batch(otslam_volume* v, int frames_per_batch);
+
+/* ---- per-frame integration: RGBDImage.create_from_color_and_depth(depth_scale, depth_trunc,
+ *      convert_rgb_to_intensity=False) + volume.integrate(rgbd, intrinsic, extrinsic)
+ *      (3d_model/reconstruct_rgbd.py:99-107).  depth: H*W u16 (raw units), rgb: H*W*3 u8,
+ *      intr = {fx, fy, cx, cy}, extrinsic = world->camera. */
+int otslam_volume_integrate_u16(otslam_volume* v, const uint16_t* depth, const uint8_t* rgb, int width, int height,
+                                const double intr[4], const double extrinsic[16], double depth_scale,
+                                double depth_trunc);
+/* same with an already converted f32 metre depth image (what RGBDImage.depth holds) */
+int otslam_volume_integrate_f32(otslam_volume* v, const float* depth_m, const uint8_t* rgb, int width, int height,
+                                const double intr[4], const double extrinsic[16]);
+/* the whole frame loop of reconstruct_object() (reconstruct_rgbd.py:86-109) in one call:
+ * n frames, frame order preserved; depth [n][H][W], rgb [n][H][W][3], extrinsics [n][16].
+ * memory = OTSLAM_MEM_HOST (pinned or pageable; copies are pipelined with compute) or
+ * OTSLAM_MEM_DEVICE (buffers already resident in HBM). */
+int otslam_volume_integrate_batch(otslam_volume* v, int n_frames, const uint16_t* depth, const uint8_t* rgb,
+                                  int width, int height, const double intr[4], const double* extrinsics,
+                                  double depth_scale, double depth_trunc, int memory);
+
+/* ---- inspection / checkpoint (parity dumps) */
+int otslam_volume_num_blocks(otslam_volume* v, int64_t* n_blocks);
+/* blocks sorted lexicographically by key; voxel index x*256+y*16+z; colour on the 0..255 scale.
+ * keys [n][3], tsdf/weight [n][4096], color [n][4096][3]; any pointer may be NULL. */
+int otslam_volume_export_blocks(otslam_volume* v, int32_t* keys, float* tsdf, float* weight, float* color);
+/* sum of all voxel weights (== number of voxel updates since reset) and voxels with weight > 0 */
+int otslam_volume_stats(otslam_volume* v, int64_t* n_blocks, uint64_t* weight_sum, uint64_t* n_observed);
+
+/* ---- surface extraction: volume.extract_triangle_mesh() (reconstruct_rgbd.py:112) followed by
+ *      mesh.compute_vertex_normals() (reconstruct_rgbd.py:113).  extract runs the kernels and
+ *      keeps the result on the device; copy fetches it.  edge_keys [nv][4] = global voxel (X,Y,Z)
+ *      + axis of each vertex's lattice edge (canonical order for comparisons); nullable outputs. */
+int otslam_volume_extract_mesh(otslam_volume* v, int64_t* n_vertices, int64_t* n_faces);
+int otslam_volume_mesh_copy(otslam_volume* v, double* vertices, double* colors, double* normals, int32_t* faces,
+                            int32_t* edge_keys);
+/* volume.extract_point_cloud() (named by north_star; zero crossings along +x/+y/+z) */
+int otslam_volume_extract_points(otslam_volume* v, int64_t* n_points);
+int otslam_volume_points_copy(otslam_volume* v, double* points, double* colors, int32_t* edge_keys);
+
+/* ---- stateless image / cloud operators (host in, host out) */
+/* RGBDImage.create_from_color_and_depth depth half (reconstruct_rgbd.py:99-104) */
+int otslam_depth_convert(const uint16_t* depth, int64_t n, double depth_scale, double depth_trunc, float* out,
+                         int device);
+/* PointCloud.create_from_rgbd_image (3d_model/check_one_frame.py:27); points/colors sized H*W*3 */
+int otslam_backproject_rgbd(const float* depth_m, const uint8_t* rgb, int width, int height, const double intr[4],
+                            const double extrinsic[16], double* points, double* colors, int64_t* n_points,
+                            int device);
+/* TriangleMesh.compute_vertex_normals (reconstruct_rgbd.py:113) */
+int otslam_mesh_vertex_normals(const double* vertices, int64_t n_vertices, const int32_t* faces, int64_t n_faces,
+                               double* normals, int device);
+/* TriangleMesh.sample_points_uniformly(number_of_points) (reconstruct_rgbd_filter.py:123);
+ * colors / normals (and their outputs) nullable */
+int otslam_mesh_sample_uniform(const double* vertices, const double* colors, const double* normals,
+                               int64_t n_vertices, const int32_t* faces, int64_t n_faces, int64_t n_samples,
+                               uint64_t seed, double* out_points, double* out_colors, double* out_normals,
+                               int device);
+/* mask = points[:,2] >= zmin; rebuild (reconstruct_rgbd_filter.py:126-132) */
+int otslam_cloud_zfilter(const double* points, const double* colors, int64_t n, double zmin, double* out_points,
+                         double* out_colors, int64_t* n_out, int device);
+/* PointCloud.voxel_down_sample (check_one_frame.py:28); outputs sized n, sorted by voxel key */
+int otslam_cloud_voxel_down_sample(const double* points, const double* colors, int64_t n, double voxel_size,
+                                   double* out_points, double* out_colors, int32_t* out_keys, int32_t* out_counts,
+                                   int64_t* n_out, int device);
+/* PointCloud.remove_statistical_outlier(nb_neighbors, std_ratio) (north_star); out_indices sized n */
+int otslam_cloud_remove_statistical_outlier(const double* points, int64_t n, int nb_neighbors, double std_ratio,
+                                            int64_t* out_indices, int64_t* n_out, double* mean_dist, int device);
+/* create_map_cloud's pixel loop (fusion/hybrid_map.py:45-55); out sized w*h*3 (or NULL to count) */
+int otslam_grid_to_points(const uint8_t* gray, int width, int height, double resolution, double origin_x,
+                          double origin_y, int threshold, double* out_points, int64_t* n_out, int device);
+/* paint_uniform_color + `+=` concat + PLY vertex packing (fusion/hybrid_map.py:59,88-91,115,121):
+ * n_clouds clouds of counts[i] points; paint[i] = RGB in 0..1 (3 doubles per cloud) or, when
+ * paint == NULL, per-point colours colors[i]; writes 27-byte binary-PLY records. */
+int otslam_cloud_merge_pack(int n_clouds, const double* const* points, const double* const* colors,
+                            const int64_t* counts, const double* paint, uint8_t* out_records, int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

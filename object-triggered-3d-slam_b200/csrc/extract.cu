@@ -1,0 +1,608 @@
+// extract.cu -- surface extraction from the block-hashed TSDF volume on sm_100a.
+//
+// Replaces volume.extract_triangle_mesh() + mesh.compute_vertex_normals()
+// (/root/reference/3d_model/reconstruct_rgbd.py:112-113) and
+// volume.extract_point_cloud() (north_star).
+//
+// Marching cubes without a global edge->vertex hash map: every lattice edge is owned by the voxel
+// at its lower end, so "vertex exists" is one bit per (voxel, axis).
+//   mc_classify   per owned block: 17^3 tsdf tile in SMEM (neighbour planes through the block hash),
+//                 cube index per voxel, triangle count, atomicOr of the used edge bits (possibly in
+//                 the +x/+y/+z neighbour block, which exists whenever the cube is valid)
+//   mc_count      per block: popcount of its edge bits -> vertex count + per-word prefix
+//   scan          exclusive scans over blocks in sorted-key order (deterministic output order)
+//   mc_vertices   per block: one vertex per set bit, FP64 arithmetic in the reference's order
+//   mc_faces      per owned block: triangles, vertex ids by bit rank, winding swapped as in A.5
+//   normals       area-weighted face normals accumulated per vertex, normalised
+#include <algorithm>
+#include <vector>
+
+#include "volume.cuh"
+
+#define MC_TABLE_QUAL static const
+#include "mc_tables.h"
+
+namespace otslam {
+
+__device__ unsigned short d_edge_table[256];
+__device__ signed char d_tri_table[256][16];
+__device__ unsigned char d_ntri[256];
+__device__ signed char d_edge_shift[12][4];
+
+static int upload_tables() {
+    static bool done[64] = {false};
+    int dev = 0;
+    OT_CUDA(cudaGetDevice(&dev));
+    if (dev < 64 && done[dev]) return OTSLAM_OK;
+    unsigned char ntri[256];
+    for (int c = 0; c < 256; ++c) {
+        int n = 0;
+        while (n < 16 && MC_TRI_TABLE[c][n] != -1) ++n;
+        ntri[c] = (unsigned char)(n / 3);
+    }
+    OT_CUDA(cudaMemcpyToSymbol(d_edge_table, MC_EDGE_TABLE, sizeof(MC_EDGE_TABLE)));
+    OT_CUDA(cudaMemcpyToSymbol(d_tri_table, MC_TRI_TABLE, sizeof(MC_TRI_TABLE)));
+    OT_CUDA(cudaMemcpyToSymbol(d_ntri, ntri, sizeof(ntri)));
+    OT_CUDA(cudaMemcpyToSymbol(d_edge_shift, MC_EDGE_SHIFT, sizeof(MC_EDGE_SHIFT)));
+    if (dev < 64) done[dev] = true;
+    return OTSLAM_OK;
+}
+
+struct ExtractCtx {
+    const uint64_t* keys;     // hash
+    const int32_t* vals;
+    uint32_t cap_mask;
+    uint4* const* chunks;
+    const uint64_t* bkeys;    // [n] sorted block keys
+    const int32_t* bslots;    // [n] their pool slots
+    int n;
+    SlabSpec slab;
+    double vl, half;
+};
+
+__device__ __forceinline__ int find_slot(const ExtractCtx& c, uint64_t key) {
+    uint32_t h = hash_key(key) & c.cap_mask;
+    for (uint32_t probe = 0; probe <= c.cap_mask; ++probe) {
+        const uint64_t k = c.keys[h];
+        if (k == key) return c.vals[h];
+        if (k == kEmptyKey) return -1;
+        h = (h + 1) & c.cap_mask;
+    }
+    return -1;
+}
+
+// neighbour table of a block: index = dx | dy<<1 | dz<<2
+__device__ __forceinline__ void load_neighbours(const ExtractCtx& c, uint64_t key, int slot, int* nslot) {
+    if (threadIdx.x < 8) {
+        const int j = threadIdx.x;
+        int kx, ky, kz;
+        unpack_key(key, kx, ky, kz);
+        int s = slot;
+        if (j) {
+            const int nx = kx + (j & 1), ny = ky + ((j >> 1) & 1), nz = kz + ((j >> 2) & 1);
+            s = key_in_range(nx, ny, nz) ? find_slot(c, pack_key(nx, ny, nz)) : -1;
+        }
+        nslot[j] = s;
+    }
+}
+
+constexpr int kFlagWords = 3 * (kVox / 32);   // 384 words: [axis][voxel bit], voxel bit = x*256+y*16+z
+
+__global__ void __launch_bounds__(256) mc_classify_kernel(ExtractCtx c, uint32_t* flags, uint8_t* cube_idx, int* tri_count) {
+    __shared__ float tile[17 * 17 * 17];
+    __shared__ int nslot[8];
+    __shared__ int s_tris;
+    const int i = blockIdx.x;
+    const int t = threadIdx.x;
+    const uint64_t key = c.bkeys[i];
+    const int slot = c.bslots[i];
+    int kx, ky, kz;
+    unpack_key(key, kx, ky, kz);
+    if (!slab_owns(c.slab, kx, ky, kz)) {   // halo block: provides voxels, emits nothing
+        if (t == 0) tri_count[i] = 0;
+        return;
+    }
+    if (t == 0) s_tris = 0;
+    load_neighbours(c, key, slot, nslot);
+    __syncthreads();
+    const float qnan = __int_as_float(0x7fc00000);
+    for (int e = t; e < 17 * 17 * 17; e += 256) {
+        const int lz = e % 17, ly = (e / 17) % 17, lx = e / 289;
+        const int nb = (lx >> 4) | ((ly >> 4) << 1) | ((lz >> 4) << 2);
+        const int s = nslot[nb];
+        float v = qnan;                       // NaN == unobserved (weight 0) or block missing
+        if (s >= 0) {
+            const uint4 r = block_ptr(c.chunks, s)[rec_index(lx & 15, ly & 15, lz & 15)];
+            if (rec_weight(r) != 0) v = __uint_as_float(r.x);
+        }
+        tile[e] = v;
+    }
+    __syncthreads();
+    int my_tris = 0;
+    for (int k = 0; k < 16; ++k) {
+        const int x = k, y = t >> 4, z = t & 15;
+        int cube = 0;
+        bool ok = true;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            // corner q of the cube: shift[q] = ((q ^ q>>1) & 1, q>>1 & 1, q>>2 & 1)  
+            const float f = tile[((x + ((q ^ (q >> 1)) & 1)) * 17 + (y + ((q >> 1) & 1))) * 17 + (z + ((q >> 2) & 1))];
+            if (f != f) ok = false;
+            if (f < 0.f) cube |= 1 << q;
+        }
+        if (!ok || cube == 255) cube = 0;
+        cube_idx[(size_t)slot * kVox + (x * 256 + y * 16 + z)] = (uint8_t)cube;
+        if (cube) {
+            my_tris += d_ntri[cube];
+            const unsigned et = d_edge_table[cube];
+            for (int e = 0; e < 12; ++e) {
+                if (!(et & (1u << e))) continue;
+                const int ox = x + d_edge_shift[e][0], oy = y + d_edge_shift[e][1], oz = z + d_edge_shift[e][2];
+                const int axis = d_edge_shift[e][3];
+                const int nb = (ox >> 4) | ((oy >> 4) << 1) | ((oz >> 4) << 2);
+                const int os = nslot[nb];     // exists: the cube is valid, so that corner was observed
+                const int bit = (ox & 15) * 256 + (oy & 15) * 16 + (oz & 15);
+                atomicOr(flags + (size_t)os * kFlagWords + axis * (kVox / 32) + (bit >> 5), 1u << (bit & 31));
+            }
+        }
+    }
+    for (int o = 16; o; o >>= 1) my_tris += __shfl_xor_sync(0xffffffffu, my_tris, o);
+    if ((t & 31) == 0 && my_tris) atomicAdd(&s_tris, my_tris);
+    __syncthreads();
+    if (t == 0) tri_count[i] = s_tris;
+}
+
+// per block: vertex count and exclusive per-word prefix of its edge bits
+__global__ void __launch_bounds__(128) mc_count_kernel(const int32_t* __restrict__ bslots, const uint32_t* __restrict__ flags,
+                                                       uint16_t* __restrict__ word_prefix, int* __restrict__ vcount) {
+    __shared__ int warp_sum[4];
+    const int i = blockIdx.x, t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    const int slot = bslots[i];
+    const uint32_t* f = flags + (size_t)slot * kFlagWords;
+    uint16_t* wp = word_prefix + (size_t)slot * kFlagWords;
+    // thread t owns words 3t..3t+2
+    const int c0 = __popc(f[3 * t]), c1 = __popc(f[3 * t + 1]), c2 = __popc(f[3 * t + 2]);
+    int v = c0 + c1 + c2, inc = v;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+    }
+    if (lane == 31) warp_sum[wid] = inc;
+    __syncthreads();
+    int base = 0;
+    for (int w = 0; w < wid; ++w) base += warp_sum[w];
+    const int ex = base + inc - v;
+    wp[3 * t] = (uint16_t)ex;
+    wp[3 * t + 1] = (uint16_t)(ex + c0);
+    wp[3 * t + 2] = (uint16_t)(ex + c0 + c1);
+    if (t == 127) vcount[i] = base + inc;
+}
+
+// single-CTA exclusive scan (n up to a few million); total written to out[n]
+__global__ void __launch_bounds__(1024) scan_kernel(const int* __restrict__ in, int64_t* __restrict__ out, int n) {
+    __shared__ int64_t part[1024];
+    const int t = threadIdx.x;
+    const int per = (n + 1023) / 1024;
+    const int b = t * per, e = min(n, b + per);
+    int64_t s = 0;
+    for (int i = b; i < e; ++i) s += in[i];
+    part[t] = s;
+    __syncthreads();
+    if (t == 0) {
+        int64_t acc = 0;
+        for (int i = 0; i < 1024; ++i) { const int64_t v = part[i]; part[i] = acc; acc += v; }
+        out[n] = acc;
+    }
+    __syncthreads();
+    int64_t acc = part[t];
+    for (int i = b; i < e; ++i) { out[i] = acc; acc += in[i]; }
+}
+
+__global__ void scatter_base_kernel(const int32_t* __restrict__ bslots, const int64_t* __restrict__ vbase, int n,
+                                    int64_t* __restrict__ vbase_by_slot) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) vbase_by_slot[bslots[i]] = vbase[i];
+}
+
+__device__ __forceinline__ void rec_color01(const uint4& r, double* c) {
+    const uint32_t w = rec_weight(r);
+    const double dw = (double)w;
+    // colour mean = exact integer sum / count (the reference keeps an FP64 running mean), then /255
+    c[0] = __ddiv_rn(__ddiv_rn((double)(r.y & 0xFFFFFFu), dw), 255.0);
+    c[1] = __ddiv_rn(__ddiv_rn((double)(r.z & 0xFFFFFFu), dw), 255.0);
+    c[2] = __ddiv_rn(__ddiv_rn((double)(r.w & 0xFFFFFFu), dw), 255.0);
+}
+
+__global__ void __launch_bounds__(128) mc_vertices_kernel(ExtractCtx c, const uint32_t* __restrict__ flags,
+                                                          const uint16_t* __restrict__ word_prefix,
+                                                          const int64_t* __restrict__ vbase, double* __restrict__ verts,
+                                                          double* __restrict__ colors, int32_t* __restrict__ ekeys) {
+    __shared__ int nslot[8];
+    const int i = blockIdx.x, t = threadIdx.x;
+    const uint64_t key = c.bkeys[i];
+    const int slot = c.bslots[i];
+    if (vbase[i + 1] == vbase[i]) return;
+    load_neighbours(c, key, slot, nslot);
+    __syncthreads();
+    int kx, ky, kz;
+    unpack_key(key, kx, ky, kz);
+    const uint4* blk = block_ptr(c.chunks, slot);
+    for (int wi = t; wi < kFlagWords; wi += 128) {
+        uint32_t bits = flags[(size_t)slot * kFlagWords + wi];
+        if (!bits) continue;
+        const int axis = wi / (kVox / 32);
+        int64_t vid = vbase[i] + word_prefix[(size_t)slot * kFlagWords + wi];
+        for (; bits; bits &= bits - 1, ++vid) {
+            const int vox = (wi % (kVox / 32)) * 32 + (__ffs(bits) - 1);
+            const int x = vox >> 8, y = (vox >> 4) & 15, z = vox & 15;
+            int q[3] = {x, y, z};
+            q[axis] += 1;
+            const int nb = (q[0] >> 4) | ((q[1] >> 4) << 1) | ((q[2] >> 4) << 2);
+            const uint4 r0 = blk[rec_index(x, y, z)];
+            const uint4 r1 = block_ptr(c.chunks, nslot[nb])[rec_index(q[0] & 15, q[1] & 15, q[2] & 15)];
+            const double f0 = fabs((double)__uint_as_float(r0.x)), f1 = fabs((double)__uint_as_float(r1.x));
+            const int g[3] = {kx * kRes + x, ky * kRes + y, kz * kRes + z};
+            double pt[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) pt[k] = __dadd_rn(c.half, __dmul_rn(c.vl, (double)g[k]));
+            const double fs = __dadd_rn(f0, f1);
+            pt[axis] = __dadd_rn(pt[axis], __ddiv_rn(__dmul_rn(f0, c.vl), fs));
+            double c0[3], c1[3];
+            rec_color01(r0, c0);
+            rec_color01(r1, c1);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                verts[3 * vid + k] = pt[k];
+                colors[3 * vid + k] = __ddiv_rn(__dadd_rn(__dmul_rn(f1, c0[k]), __dmul_rn(f0, c1[k])), fs);
+            }
+            if (ekeys) {
+                ekeys[4 * vid] = g[0]; ekeys[4 * vid + 1] = g[1]; ekeys[4 * vid + 2] = g[2]; ekeys[4 * vid + 3] = axis;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) mc_faces_kernel(ExtractCtx c, const uint32_t* __restrict__ flags,
+                                                       const uint16_t* __restrict__ word_prefix,
+                                                       const int64_t* __restrict__ vbase_by_slot,
+                                                       const uint8_t* __restrict__ cube_idx,
+                                                       const int64_t* __restrict__ fbase, int32_t* __restrict__ faces) {
+    __shared__ int nslot[8];
+    __shared__ int warp_sum[8];
+    const int i = blockIdx.x, t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    if (fbase[i + 1] == fbase[i]) return;
+    const uint64_t key = c.bkeys[i];
+    const int slot = c.bslots[i];
+    load_neighbours(c, key, slot, nslot);
+    // thread t owns voxels 16t..16t+15 (reference order x*256+y*16+z)
+    const uint8_t* ci = cube_idx + (size_t)slot * kVox + 16 * t;
+    const uint4 packed = *reinterpret_cast<const uint4*>(ci);
+    const uint32_t pw[4] = {packed.x, packed.y, packed.z, packed.w};
+    int mine = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) mine += d_ntri[(pw[k >> 2] >> (8 * (k & 3))) & 0xFF];
+    int inc = mine;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+    }
+    if (lane == 31) warp_sum[wid] = inc;
+    __syncthreads();
+    int base = 0;
+    for (int w = 0; w < wid; ++w) base += warp_sum[w];
+    int64_t fo = fbase[i] + base + inc - mine;
+    for (int k = 0; k < 16; ++k) {
+        const int cube = (pw[k >> 2] >> (8 * (k & 3))) & 0xFF;
+        if (!cube) continue;
+        const int vox = 16 * t + k;
+        const int x = vox >> 8, y = (vox >> 4) & 15, z = vox & 15;
+        const int nt = d_ntri[cube];
+        for (int tr = 0; tr < nt; ++tr) {
+            int vid[3];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const int e = d_tri_table[cube][3 * tr + j];
+                const int ox = x + d_edge_shift[e][0], oy = y + d_edge_shift[e][1], oz = z + d_edge_shift[e][2];
+                const int axis = d_edge_shift[e][3];
+                const int os = nslot[(ox >> 4) | ((oy >> 4) << 1) | ((oz >> 4) << 2)];
+                const int bit = (ox & 15) * 256 + (oy & 15) * 16 + (oz & 15);
+                const int wi = axis * (kVox / 32) + (bit >> 5);
+                const uint32_t wbits = flags[(size_t)os * kFlagWords + wi];
+                vid[j] = (int)(vbase_by_slot[os] + word_prefix[(size_t)os * kFlagWords + wi] +
+                               __popc(wbits & ((1u << (bit & 31)) - 1u)));
+            }
+            faces[3 * fo] = vid[0];
+            faces[3 * fo + 1] = vid[2];   // winding swapped w.r.t. the table
+            faces[3 * fo + 2] = vid[1];
+            ++fo;
+        }
+    }
+}
+
+// ---- compute_vertex_normals
+__global__ void __launch_bounds__(256) face_normals_kernel(const double* __restrict__ verts, const int32_t* __restrict__ faces,
+                                                           int64_t nf, double* __restrict__ normals) {
+    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nf) return;
+    const int a = faces[3 * f], b = faces[3 * f + 1], cidx = faces[3 * f + 2];
+    double e1[3], e2[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        e1[k] = __dsub_rn(verts[3 * (size_t)b + k], verts[3 * (size_t)a + k]);
+        e2[k] = __dsub_rn(verts[3 * (size_t)cidx + k], verts[3 * (size_t)a + k]);
+    }
+    const double n[3] = {__dsub_rn(__dmul_rn(e1[1], e2[2]), __dmul_rn(e1[2], e2[1])),
+                         __dsub_rn(__dmul_rn(e1[2], e2[0]), __dmul_rn(e1[0], e2[2])),
+                         __dsub_rn(__dmul_rn(e1[0], e2[1]), __dmul_rn(e1[1], e2[0]))};
+    const int v[3] = {a, b, cidx};
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) atomicAdd(normals + 3 * (size_t)v[j] + k, n[k]);
+}
+
+__global__ void __launch_bounds__(256) normalize_kernel(double* __restrict__ normals, int64_t nv) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nv) return;
+    double* n = normals + 3 * i;
+    const double l = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(n[0], n[0]), __dmul_rn(n[1], n[1])), __dmul_rn(n[2], n[2])));
+    if (l > 0.0) {
+        n[0] = __ddiv_rn(n[0], l); n[1] = __ddiv_rn(n[1], l); n[2] = __ddiv_rn(n[2], l);
+    } else {
+        n[0] = 0.0; n[1] = 0.0; n[2] = 1.0;
+    }
+}
+
+int device_vertex_normals(const double* d_verts, int64_t nv, const int32_t* d_faces, int64_t nf, double* d_normals,
+                          cudaStream_t s) {
+    if (nv == 0) return OTSLAM_OK;
+    OT_CUDA(cudaMemsetAsync(d_normals, 0, (size_t)nv * 24, s));
+    if (nf > 0) {
+        face_normals_kernel<<<(unsigned)((nf + 255) / 256), 256, 0, s>>>(d_verts, d_faces, nf, d_normals);
+        OT_LAUNCHED();
+    }
+    normalize_kernel<<<(unsigned)((nv + 255) / 256), 256, 0, s>>>(d_normals, nv);
+    OT_LAUNCHED();
+    return OTSLAM_OK;
+}
+
+// ---- extract_point_cloud
+__global__ void __launch_bounds__(256) pc_extract_kernel(ExtractCtx c, const int64_t* __restrict__ pbase, int* __restrict__ pcount,
+                                                         double* __restrict__ pts, double* __restrict__ cols,
+                                                         int32_t* __restrict__ ekeys) {
+    __shared__ int nslot[8];
+    __shared__ int warp_sum[8];
+    const int i = blockIdx.x, t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    const uint64_t key = c.bkeys[i];
+    const int slot = c.bslots[i];
+    int kx, ky, kz;
+    unpack_key(key, kx, ky, kz);
+    const bool count_only = (pbase == nullptr);
+    if (!slab_owns(c.slab, kx, ky, kz)) {
+        if (count_only && t == 0) pcount[i] = 0;
+        return;
+    }
+    if (!count_only && pbase[i + 1] == pbase[i]) return;
+    load_neighbours(c, key, slot, nslot);
+    __syncthreads();
+    const uint4* blk = block_ptr(c.chunks, slot);
+    // thread t owns voxels 16t..16t+15 in reference order; pass 1 counts, pass 2 emits
+    uint32_t hits[2] = {0, 0};   // 3 bits per voxel
+    int mine = 0;
+    for (int k = 0; k < 16; ++k) {
+        const int vox = 16 * t + k;
+        const int x = vox >> 8, y = (vox >> 4) & 15, z = vox & 15;
+        const uint4 r0 = blk[rec_index(x, y, z)];
+        const float f0 = __uint_as_float(r0.x);
+        if (rec_weight(r0) == 0 || !(f0 < 0.98f && f0 >= -0.98f)) continue;
+        for (int a = 0; a < 3; ++a) {
+            int q[3] = {x, y, z};
+            q[a] += 1;
+            const int s = nslot[(q[0] >> 4) | ((q[1] >> 4) << 1) | ((q[2] >> 4) << 2)];
+            if (s < 0) continue;
+            const uint4 r1 = block_ptr(c.chunks, s)[rec_index(q[0] & 15, q[1] & 15, q[2] & 15)];
+            const float f1 = __uint_as_float(r1.x);
+            if (rec_weight(r1) == 0 || !(f1 < 0.98f && f1 >= -0.98f) || !(__fmul_rn(f0, f1) < 0.f)) continue;
+            hits[k >> 3] |= 1u << (3 * (k & 7) + a);
+            ++mine;
+        }
+    }
+    int inc = mine;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+    }
+    if (lane == 31) warp_sum[wid] = inc;
+    __syncthreads();
+    int base = 0;
+    for (int w = 0; w < wid; ++w) base += warp_sum[w];
+    if (count_only) {
+        if (t == 255) pcount[i] = base + inc;
+        return;
+    }
+    int64_t o = pbase[i] + base + inc - mine;
+    for (int k = 0; k < 16; ++k) {
+        const uint32_t h = (hits[k >> 3] >> (3 * (k & 7))) & 7u;
+        if (!h) continue;
+        const int vox = 16 * t + k;
+        const int x = vox >> 8, y = (vox >> 4) & 15, z = vox & 15;
+        const uint4 r0 = blk[rec_index(x, y, z)];
+        const double r0a = fabs((double)__uint_as_float(r0.x));
+        const int g[3] = {kx * kRes + x, ky * kRes + y, kz * kRes + z};
+        double p0[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) p0[j] = __dadd_rn(c.half, __dmul_rn(c.vl, (double)g[j]));
+        const uint32_t w0 = rec_weight(r0);
+        for (int a = 0; a < 3; ++a) {
+            if (!(h & (1u << a))) continue;
+            int q[3] = {x, y, z};
+            q[a] += 1;
+            const int s = nslot[(q[0] >> 4) | ((q[1] >> 4) << 1) | ((q[2] >> 4) << 2)];
+            const uint4 r1 = block_ptr(c.chunks, s)[rec_index(q[0] & 15, q[1] & 15, q[2] & 15)];
+            const double r1a = fabs((double)__uint_as_float(r1.x));
+            const uint32_t w1 = rec_weight(r1);
+            const double rs = __dadd_rn(r0a, r1a);
+            double p[3] = {p0[0], p0[1], p0[2]};
+            const double p1a = __dadd_rn(p0[a], c.vl);
+            p[a] = __ddiv_rn(__dadd_rn(__dmul_rn(p0[a], r1a), __dmul_rn(p1a, r0a)), rs);
+            const uint32_t s0[3] = {r0.y & 0xFFFFFFu, r0.z & 0xFFFFFFu, r0.w & 0xFFFFFFu};
+            const uint32_t s1[3] = {r1.y & 0xFFFFFFu, r1.z & 0xFFFFFFu, r1.w & 0xFFFFFFu};
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                pts[3 * o + j] = p[j];
+                const double c0 = __ddiv_rn((double)s0[j], (double)w0), c1 = __ddiv_rn((double)s1[j], (double)w1);
+                cols[3 * o + j] = __ddiv_rn(__ddiv_rn(__dadd_rn(__dmul_rn(c0, r1a), __dmul_rn(c1, r0a)), rs), 255.0);
+            }
+            if (ekeys) { ekeys[4 * o] = g[0]; ekeys[4 * o + 1] = g[1]; ekeys[4 * o + 2] = g[2]; ekeys[4 * o + 3] = a; }
+            ++o;
+        }
+    }
+}
+
+static int make_ctx(otslam_volume* v, ExtractCtx& c, DevBuf<uint64_t>& dk, DevBuf<int32_t>& ds) {
+    std::vector<uint64_t> k;
+    std::vector<int32_t> s;
+    OT_TRY(volume_sorted_blocks(v, k, s));
+    OT_CUDA(dk.alloc(k.size()));
+    OT_CUDA(ds.alloc(s.size()));
+    if (!k.empty()) {
+        OT_CUDA(cudaMemcpyAsync(dk.p, k.data(), k.size() * 8, cudaMemcpyHostToDevice, v->stream));
+        OT_CUDA(cudaMemcpyAsync(ds.p, s.data(), s.size() * 4, cudaMemcpyHostToDevice, v->stream));
+        OT_CUDA(cudaStreamSynchronize(v->stream));
+    }
+    c.keys = v->d_keys; c.vals = v->d_vals; c.cap_mask = v->cap - 1; c.chunks = v->d_chunks;
+    c.bkeys = dk.p; c.bslots = ds.p; c.n = (int)k.size(); c.slab = v->slab;
+    c.vl = v->voxel_length; c.half = 0.5 * v->voxel_length;
+    return OTSLAM_OK;
+}
+
+}  // namespace otslam
+
+using namespace otslam;
+
+extern "C" {
+
+int otslam_volume_extract_mesh(otslam_volume* v, int64_t* n_vertices, int64_t* n_faces) {
+    if (!v || !n_vertices || !n_faces) return set_error(OTSLAM_ERR_INVALID, "null argument");
+    OT_TRY(use_device(v->device));
+    OT_TRY(upload_tables());
+    v->mesh.release();
+    *n_vertices = 0; *n_faces = 0;
+    ExtractCtx c;
+    DevBuf<uint64_t> dk;
+    DevBuf<int32_t> ds;
+    OT_TRY(make_ctx(v, c, dk, ds));
+    const int n = c.n;
+    if (n == 0) return OTSLAM_OK;
+    cudaStream_t s = v->stream;
+    DevBuf<uint32_t> flags;
+    DevBuf<uint16_t> wprefix;
+    DevBuf<uint8_t> cube;
+    DevBuf<int> tri_count, vcount;
+    DevBuf<int64_t> vbase, fbase, vbase_slot;
+    OT_CUDA(flags.alloc((size_t)n * kFlagWords));
+    OT_CUDA(wprefix.alloc((size_t)n * kFlagWords));
+    OT_CUDA(cube.alloc((size_t)n * kVox));
+    OT_CUDA(tri_count.alloc(n)); OT_CUDA(vcount.alloc(n));
+    OT_CUDA(vbase.alloc(n + 1)); OT_CUDA(fbase.alloc(n + 1)); OT_CUDA(vbase_slot.alloc(n));
+    OT_CUDA(cudaMemsetAsync(flags.p, 0, (size_t)n * kFlagWords * 4, s));
+    mc_classify_kernel<<<n, 256, 0, s>>>(c, flags.p, cube.p, tri_count.p);
+    OT_LAUNCHED();
+    mc_count_kernel<<<n, 128, 0, s>>>(c.bslots, flags.p, wprefix.p, vcount.p);
+    OT_LAUNCHED();
+    scan_kernel<<<1, 1024, 0, s>>>(vcount.p, vbase.p, n);
+    OT_LAUNCHED();
+    scan_kernel<<<1, 1024, 0, s>>>(tri_count.p, fbase.p, n);
+    OT_LAUNCHED();
+    scatter_base_kernel<<<(n + 255) / 256, 256, 0, s>>>(c.bslots, vbase.p, n, vbase_slot.p);
+    OT_LAUNCHED();
+    int64_t nv = 0, nf = 0;
+    OT_CUDA(cudaMemcpyAsync(&nv, vbase.p + n, 8, cudaMemcpyDeviceToHost, s));
+    OT_CUDA(cudaMemcpyAsync(&nf, fbase.p + n, 8, cudaMemcpyDeviceToHost, s));
+    OT_CUDA(cudaStreamSynchronize(s));
+    if (nv > 0x7fffffffLL || nf > 0x7fffffffLL) return set_error(OTSLAM_ERR_OVERFLOW, "mesh exceeds int32 indices");
+    MeshResult& m = v->mesh;
+    m.nv = nv; m.nf = nf;
+    if (nv > 0) {
+        OT_CUDA(cudaMalloc((void**)&m.d_verts, (size_t)nv * 24));
+        OT_CUDA(cudaMalloc((void**)&m.d_colors, (size_t)nv * 24));
+        OT_CUDA(cudaMalloc((void**)&m.d_normals, (size_t)nv * 24));
+        OT_CUDA(cudaMalloc((void**)&m.d_ekeys, (size_t)nv * 16));
+        OT_CUDA(cudaMalloc((void**)&m.d_faces, (size_t)std::max<int64_t>(nf, 1) * 12));
+        mc_vertices_kernel<<<n, 128, 0, s>>>(c, flags.p, wprefix.p, vbase.p, m.d_verts, m.d_colors, m.d_ekeys);
+        OT_LAUNCHED();
+        if (nf > 0) {
+            mc_faces_kernel<<<n, 256, 0, s>>>(c, flags.p, wprefix.p, vbase_slot.p, cube.p, fbase.p, m.d_faces);
+            OT_LAUNCHED();
+        }
+        OT_TRY(device_vertex_normals(m.d_verts, nv, m.d_faces, nf, m.d_normals, s));
+    }
+    OT_CUDA(cudaStreamSynchronize(s));
+    *n_vertices = nv; *n_faces = nf;
+    return OTSLAM_OK;
+}
+
+int otslam_volume_mesh_copy(otslam_volume* v, double* vertices, double* colors, double* normals, int32_t* faces,
+                            int32_t* edge_keys) {
+    if (!v) return set_error(OTSLAM_ERR_INVALID, "null volume");
+    OT_TRY(use_device(v->device));
+    const MeshResult& m = v->mesh;
+    if (m.nv > 0) {
+        if (vertices) OT_CUDA(cudaMemcpy(vertices, m.d_verts, (size_t)m.nv * 24, cudaMemcpyDeviceToHost));
+        if (colors) OT_CUDA(cudaMemcpy(colors, m.d_colors, (size_t)m.nv * 24, cudaMemcpyDeviceToHost));
+        if (normals) OT_CUDA(cudaMemcpy(normals, m.d_normals, (size_t)m.nv * 24, cudaMemcpyDeviceToHost));
+        if (edge_keys) OT_CUDA(cudaMemcpy(edge_keys, m.d_ekeys, (size_t)m.nv * 16, cudaMemcpyDeviceToHost));
+    }
+    if (m.nf > 0 && faces) OT_CUDA(cudaMemcpy(faces, m.d_faces, (size_t)m.nf * 12, cudaMemcpyDeviceToHost));
+    return OTSLAM_OK;
+}
+
+int otslam_volume_extract_points(otslam_volume* v, int64_t* n_points) {
+    if (!v || !n_points) return set_error(OTSLAM_ERR_INVALID, "null argument");
+    OT_TRY(use_device(v->device));
+    v->points.release();
+    *n_points = 0;
+    ExtractCtx c;
+    DevBuf<uint64_t> dk;
+    DevBuf<int32_t> ds;
+    OT_TRY(make_ctx(v, c, dk, ds));
+    const int n = c.n;
+    if (n == 0) return OTSLAM_OK;
+    cudaStream_t s = v->stream;
+    DevBuf<int> pcount;
+    DevBuf<int64_t> pbase;
+    OT_CUDA(pcount.alloc(n)); OT_CUDA(pbase.alloc(n + 1));
+    pc_extract_kernel<<<n, 256, 0, s>>>(c, nullptr, pcount.p, nullptr, nullptr, nullptr);
+    OT_LAUNCHED();
+    scan_kernel<<<1, 1024, 0, s>>>(pcount.p, pbase.p, n);
+    OT_LAUNCHED();
+    int64_t np = 0;
+    OT_CUDA(cudaMemcpyAsync(&np, pbase.p + n, 8, cudaMemcpyDeviceToHost, s));
+    OT_CUDA(cudaStreamSynchronize(s));
+    PointsResult& p = v->points;
+    p.n = np;
+    if (np > 0) {
+        OT_CUDA(cudaMalloc((void**)&p.d_pts, (size_t)np * 24));
+        OT_CUDA(cudaMalloc((void**)&p.d_cols, (size_t)np * 24));
+        OT_CUDA(cudaMalloc((void**)&p.d_ekeys, (size_t)np * 16));
+        pc_extract_kernel<<<n, 256, 0, s>>>(c, pbase.p, nullptr, p.d_pts, p.d_cols, p.d_ekeys);
+        OT_LAUNCHED();
+        OT_CUDA(cudaStreamSynchronize(s));
+    }
+    *n_points = np;
+    return OTSLAM_OK;
+}
+
+int otslam_volume_points_copy(otslam_volume* v, double* points, double* colors, int32_t* edge_keys) {
+    if (!v) return set_error(OTSLAM_ERR_INVALID, "null volume");
+    OT_TRY(use_device(v->device));
+    const PointsResult& p = v->points;
+    if (p.n > 0) {
+        if (points) OT_CUDA(cudaMemcpy(points, p.d_pts, (size_t)p.n * 24, cudaMemcpyDeviceToHost));
+        if (colors) OT_CUDA(cudaMemcpy(colors, p.d_cols, (size_t)p.n * 24, cudaMemcpyDeviceToHost));
+        if (edge_keys) OT_CUDA(cudaMemcpy(edge_keys, p.d_ekeys, (size_t)p.n * 16, cudaMemcpyDeviceToHost));
+    }
+    return OTSLAM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,89 @@
+// volume.cuh -- host-side state of one ScalableTSDFVolume replacement (see volume.cu).
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+
+namespace otslam {
+
+constexpr int kMaxBatch = 32;   // frames fused per block residency (one bit each in the entry mask)
+
+// per-frame constants consumed by the allocation (FP64 pose) and integration (FP32 extrinsic) kernels
+struct FrameDev {
+    float E[12];      // rows 0..2 of extrinsic.cast<float>()           
+    float es[3];      // (E * voxel_length).col(2): the per-z increment  
+    float pad;
+    double pose[12];  // rows 0..2 of camera_pose = extrinsic.inverse()  
+};
+static_assert(sizeof(FrameDev) == 160, "FrameDev layout");
+
+enum CounterIdx { kPoolCount = 0, kListCount = 1, kFlags = 2, kNumCounters = 4 };
+enum Flags { kFlagHashFull = 1, kFlagKeyRange = 2, kFlagBoxTooLarge = 4 };
+
+struct MeshResult {
+    int64_t nv = 0, nf = 0;
+    double* d_verts = nullptr;    // [nv][3]
+    double* d_colors = nullptr;   // [nv][3]
+    double* d_normals = nullptr;  // [nv][3]
+    int32_t* d_faces = nullptr;   // [nf][3]
+    int32_t* d_ekeys = nullptr;   // [nv][4]
+    void release();
+};
+struct PointsResult {
+    int64_t n = 0;
+    double* d_pts = nullptr;
+    double* d_cols = nullptr;
+    int32_t* d_ekeys = nullptr;
+    void release();
+};
+
+}  // namespace otslam
+
+struct otslam_volume {
+    int device = 0;
+    double voxel_length = 0, sdf_trunc = 0, unit_length = 0;
+    int color_type = OTSLAM_COLOR_RGB8;
+    otslam::SlabSpec slab{0, 8, 1, 0};
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    bool own_stream = true;
+    int batch = otslam::kMaxBatch;
+    int64_t frames_integrated = 0;
+
+    // block hash: open addressing, entry index is the handle used by the per-batch work list
+    uint32_t cap = 0;
+    uint64_t* d_keys = nullptr;
+    int32_t* d_vals = nullptr;     // entry -> pool slot
+    uint32_t* d_masks = nullptr;   // entry -> bit f set when frame f of the current batch touches it
+    int32_t* d_list = nullptr;     // entries touched by the current batch (each once)
+
+    // block pool: chunks of kChunkBlocks blocks, 64 KiB per block
+    std::vector<uint4*> chunks;
+    uint4** d_chunks = nullptr;
+    int64_t n_blocks = 0;          // host mirror of the pool counter
+
+    int* d_counters = nullptr;
+    int* h_counters = nullptr;     // pinned
+
+    // frame staging (double buffered)
+    uint16_t* d_raw_depth[2] = {nullptr, nullptr};
+    uint8_t* d_raw_rgb[2] = {nullptr, nullptr};
+    uint2* d_packed[2] = {nullptr, nullptr};
+    size_t raw_frames_cap = 0, raw_px_cap = 0, packed_cap = 0;
+    size_t raw_depth_bytes_per_px = 2;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_raw_free[2] = {nullptr, nullptr};
+    otslam::FrameDev* d_frames[2] = {nullptr, nullptr};
+    otslam::FrameDev* h_frames = nullptr;  // pinned [2][kMaxBatch]
+
+    // depth->camera-distance multiplier image, cached per intrinsics
+    float* d_mult = nullptr;
+    int mult_w = 0, mult_h = 0;
+    double mult_intr[4] = {0, 0, 0, 0};
+
+    otslam::MeshResult mesh;
+    otslam::PointsResult points;
+};
+
+namespace otslam {
+// implemented in volume.cu, used by extract.cu
+int volume_sorted_blocks(otslam_volume* v, std::vector<uint64_t>& keys, std::vector<int32_t>& slots);
+}

@@ -1,0 +1,120 @@
+"""Host-side handle of one GPU ScalableTSDFVolume (thin wrapper over the C ABI).
+
+Mirrors o3d.pipelines.integration.ScalableTSDFVolume as used at
+/root/reference/3d_model/reconstruct_rgbd.py:79-83,107,112.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+class TSDFVolume:
+    def __init__(self, voxel_length, sdf_trunc, color=True, device=0, slab=None):
+        self.voxel_length, self.sdf_trunc, self.device = float(voxel_length), float(sdf_trunc), int(device)
+        self._h = C.c_void_p()
+        spec = None
+        if slab is not None:
+            spec = C.byref(_lib.SlabSpec(*[int(x) for x in slab]))
+        _lib.check(_lib.lib.otslam_volume_create(self.voxel_length, self.sdf_trunc,
+                                                 _lib.COLOR_RGB8 if color else _lib.COLOR_NONE, self.device, spec,
+                                                 C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib.otslam_volume_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def reset(self):
+        _lib.check(_lib.lib.otslam_volume_reset(self._h))
+
+    def set_stream(self, cuda_stream):
+        _lib.check(_lib.lib.otslam_volume_set_stream(self._h, C.c_void_p(int(cuda_stream) if cuda_stream else 0)))
+
+    def set_batch(self, n):
+        _lib.check(_lib.lib.otslam_volume_set_batch(self._h, int(n)))
+
+    @staticmethod
+    def _intr(intr):
+        return np.ascontiguousarray(intr, np.float64).reshape(4)
+
+    def integrate_u16(self, depth, rgb, intr, extrinsic, depth_scale=1000.0, depth_trunc=3.0):
+        d = np.ascontiguousarray(depth, np.uint16)
+        c = None if rgb is None else np.ascontiguousarray(rgb, np.uint8)
+        H, W = d.shape
+        if c is not None and c.shape != (H, W, 3):
+            raise RuntimeError("[ScalableTSDFVolume::Integrate] Unsupported image format.")
+        k, e = self._intr(intr), np.ascontiguousarray(extrinsic, np.float64).reshape(16)
+        _lib.check(_lib.lib.otslam_volume_integrate_u16(self._h, _lib.ptr(d), _lib.ptr(c), W, H, _lib.ptr(k), _lib.ptr(e),
+                                                        float(depth_scale), float(depth_trunc)))
+
+    def integrate_f32(self, depth_m, rgb, intr, extrinsic):
+        d = np.ascontiguousarray(depth_m, np.float32)
+        c = None if rgb is None else np.ascontiguousarray(rgb, np.uint8)
+        H, W = d.shape
+        if c is not None and c.shape != (H, W, 3):
+            raise RuntimeError("[ScalableTSDFVolume::Integrate] Unsupported image format.")
+        k, e = self._intr(intr), np.ascontiguousarray(extrinsic, np.float64).reshape(16)
+        _lib.check(_lib.lib.otslam_volume_integrate_f32(self._h, _lib.ptr(d), _lib.ptr(c), W, H, _lib.ptr(k), _lib.ptr(e)))
+
+    def integrate_batch(self, depth, rgb, intr, extrinsics, depth_scale=1000.0, depth_trunc=3.0):
+        """depth [n,H,W] u16, rgb [n,H,W,3] u8: numpy arrays / CPU torch tensors (host path, copies
+        pipelined inside the call) or CUDA torch tensors (already resident in HBM)."""
+        n, H, W = int(depth.shape[0]), int(depth.shape[1]), int(depth.shape[2])
+        on_dev = hasattr(depth, "is_cuda") and depth.is_cuda
+        if isinstance(depth, np.ndarray):
+            depth = np.ascontiguousarray(depth, np.uint16)
+            rgb = None if rgb is None else np.ascontiguousarray(rgb, np.uint8)
+        else:
+            assert depth.is_contiguous() and (rgb is None or rgb.is_contiguous())
+            assert depth.element_size() == 2
+            assert rgb is None or (rgb.element_size() == 1 and bool(rgb.is_cuda) == bool(on_dev))
+        if rgb is not None and tuple(rgb.shape) != (n, H, W, 3):
+            raise RuntimeError("[ScalableTSDFVolume::Integrate] Unsupported image format.")
+        k = self._intr(intr)
+        e = np.ascontiguousarray(extrinsics, np.float64).reshape(n, 16)
+        _lib.check(_lib.lib.otslam_volume_integrate_batch(self._h, n, _lib.ptr(depth), _lib.ptr(rgb), W, H, _lib.ptr(k),
+                                                          _lib.ptr(e), float(depth_scale), float(depth_trunc),
+                                                          _lib.MEM_DEVICE if on_dev else _lib.MEM_HOST))
+
+    def num_blocks(self):
+        n = C.c_int64(0)
+        _lib.check(_lib.lib.otslam_volume_num_blocks(self._h, C.byref(n)))
+        return n.value
+
+    def export_blocks(self, color=True):
+        n = self.num_blocks()
+        keys = np.empty((n, 3), np.int32)
+        tsdf = np.empty((n, 4096), np.float32)
+        weight = np.empty((n, 4096), np.float32)
+        col = np.empty((n, 4096, 3), np.float32) if color else None
+        _lib.check(_lib.lib.otslam_volume_export_blocks(self._h, _lib.ptr(keys), _lib.ptr(tsdf), _lib.ptr(weight), _lib.ptr(col)))
+        return keys, tsdf, weight, col
+
+    def stats(self):
+        nb, ws, no = C.c_int64(0), C.c_uint64(0), C.c_uint64(0)
+        _lib.check(_lib.lib.otslam_volume_stats(self._h, C.byref(nb), C.byref(ws), C.byref(no)))
+        return {"n_blocks": nb.value, "weight_sum": ws.value, "n_observed": no.value}
+
+    def extract_triangle_mesh(self, normals=True):
+        nv, nf = C.c_int64(0), C.c_int64(0)
+        _lib.check(_lib.lib.otslam_volume_extract_mesh(self._h, C.byref(nv), C.byref(nf)))
+        verts = np.empty((nv.value, 3), np.float64)
+        cols = np.empty((nv.value, 3), np.float64)
+        nrm = np.empty((nv.value, 3), np.float64) if normals else None
+        faces = np.empty((nf.value, 3), np.int32)
+        ek = np.empty((nv.value, 4), np.int32)
+        _lib.check(_lib.lib.otslam_volume_mesh_copy(self._h, _lib.ptr(verts), _lib.ptr(cols), _lib.ptr(nrm), _lib.ptr(faces), _lib.ptr(ek)))
+        return verts, cols, nrm, faces, ek
+
+    def extract_point_cloud(self):
+        n = C.c_int64(0)
+        _lib.check(_lib.lib.otslam_volume_extract_points(self._h, C.byref(n)))
+        pts = np.empty((n.value, 3), np.float64)
+        cols = np.empty((n.value, 3), np.float64)
+        ek = np.empty((n.value, 4), np.int32)
+        _lib.check(_lib.lib.otslam_volume_points_copy(self._h, _lib.ptr(pts), _lib.ptr(cols), _lib.ptr(ek)))
+        return pts, cols, ek
