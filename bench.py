@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py -- RGB-D frames/s integrated (640x480, 5 mm TSDF) on B200.
+
+One "step" = the frame loop of reconstruct_object() (/root/reference/3d_model/reconstruct_rgbd.py:86-109)
+over the whole synthetic sequence, starting from a reset volume:
+    reset -> [depth convert+mask, block allocation, TSDF+colour integration] x n_frames.
+  value  : frames/s with the sequence already resident in HBM (kernel path only)
+  e2e    : same metric through the public C-ABI call with HOST (pinned) buffers, H2D copies and a
+           D2H read of the result statistics inside the timed region
+  roofline: integrate_kernel, algorithmic bytes (40 B x N_upd + 5 B x W x H per frame)
+           / CUDA-event duration of that kernel, against MEASURED_PEAKS.json
+  cpu_baseline: the oracle (CPU port of the Open3D algorithm the reference calls) on a bounded
+           sample of the same sequence, all host threads
+
+Multi-GPU (torchrun, one rank per GPU): every rank receives every frame and integrates only its
+own spatial slab -- total work fixed => "scaling": "strong"; no per-frame collective.
+`--impl reference` times the reference's CPU path (the oracle port; Open3D itself is not
+installable here) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "RGB-D frames/s integrated (640x480, 5mm TSDF)"
+UNIT = "frames/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=300)
+    ap.add_argument("--scene", default="table")
+    ap.add_argument("--voxel", type=float, default=0.005)
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--hd", action="store_true", help="1280x720 / 2 mm large-room config (SURVEY 8d config 4)")
+    ap.add_argument("--cpu-frames", type=int, default=0, help="oracle sample size (0 = auto)")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    if a.hd:
+        return f"large-room synthetic sequence 1280x720 x {a.frames} frames, voxel {a.voxel*1000:g} mm / trunc {4*a.voxel*1000:g} mm"
+    return (f"reconstruct_rgbd.py frame loop: {a.frames}-frame synthetic '{a.scene}' sequence 640x480, "
+            f"voxel {a.voxel*1000:g} mm / trunc {4*a.voxel*1000:g} mm, depth_trunc 3 m")
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_sample(a, seq_np, cores_hint=None):
+    """Time the oracle on a bounded sample (every k-th frame) of the same sequence."""
+    from oracle import oracle
+    depth, rgb, extr, fxfycxcy = seq_np
+    n = len(depth)
+    cores = oracle.num_threads()
+    want = a.cpu_frames or max(8, min(n, 6 * cores))
+    step = max(1, n // want)
+    idx = list(range(0, n, step))[:want]
+    vol = oracle.Volume(a.voxel, 4 * a.voxel)
+    # warm the first frame's allocations outside the timed region? No: allocation is part of the loop.
+    t0 = time.perf_counter()
+    for k in idx:
+        d = oracle.depth_convert(depth[k], 1000.0, 3.0)
+        vol.integrate(d, rgb[k], fxfycxcy, extr[k])
+    dt = time.perf_counter() - t0
+    return {"value": len(idx) / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{len(idx)} frames (every {step}th of {n}) of the same sequence, depth convert + integrate, "
+                      f"{dt:.1f} s of CPU work"}, dt, len(idx)
+
+
+def make_sequence(a, device):
+    from otslam_b200 import synth
+    intr = synth.HD_INTRINSICS if a.hd else synth.REF_INTRINSICS
+    scene = "room" if a.hd else a.scene
+    return synth.make_sequence(scene, a.frames, intr=intr, device=device)
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    seq = make_sequence(a, "cpu")
+    d, c = seq.numpy()
+    seq_np = (d, c, seq.extrinsic, seq.fxfycxcy)
+    # each step = a bounded sample of the workload
+    res = None
+    vals = []
+    for s in range(a.warmup + a.steps):
+        res, dt, nf = cpu_sample(a, seq_np)
+        if s >= a.warmup:
+            vals.append((nf, dt))
+    tot_f = sum(v[0] for v in vals); tot_t = sum(v[1] for v in vals)
+    value = tot_f / tot_t
+    res["value"] = value
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": 1e3 * tot_t / max(1, a.steps), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(a), "note": "reference CPU path = oracle port of Open3D legacy "
+                       "ScalableTSDFVolume (open3d itself is not installable offline); each step is a bounded sample"},
+            "cpu_baseline": res,
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def run_ours(a):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from otslam_b200 import _lib
+    from otslam_b200.volume import TSDFVolume
+
+    seq = make_sequence(a, f"cuda:{local}")
+    W, H = seq.intr[0], seq.intr[1]
+    n = len(seq)
+    depth_dev, rgb_dev = seq.depth.contiguous(), seq.rgb.contiguous()
+    slab = None if world == 1 else (0, 8, world, rank)
+    vol = TSDFVolume(a.voxel, 4 * a.voxel, device=local, slab=slab)
+    vol.set_batch(a.batch)
+    stream = torch.cuda.Stream()
+    vol.set_stream(stream.cuda_stream)
+    torch.cuda.synchronize()
+
+    def step():
+        vol.reset()
+        vol.integrate_batch(depth_dev, rgb_dev, seq.fxfycxcy, seq.extrinsic)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        for _ in range(a.warmup):
+            step()
+        stats = vol.stats()
+        n_upd = stats["weight_sum"]
+        barrier()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        vol.profile(True)
+        l0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for _ in range(a.steps):
+            step()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = _lib.launch_count() - l0
+        prof = vol.profile(False)
+        clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = n * a.steps / (ms_max * 1e-3)
+
+    # ---- roofline of the dominant kernel (this rank's slab)
+    peak, peak_src = peaks()
+    k4_ms, k4_launches = prof["integrate"]
+    bytes_step = 40.0 * n_upd + 5.0 * W * H * n
+    bytes_per_launch = bytes_step * a.steps / max(1, k4_launches)
+    k4_avg_ms = k4_ms / max(1, k4_launches)
+    achieved = bytes_per_launch / (k4_avg_ms * 1e-3) / 1e9 if k4_avg_ms > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "integrate_kernel_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "integrate_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": bytes_per_launch, "launch_ms": k4_avg_ms,
+                "launches_per_step": k4_launches / max(1, a.steps),
+                "n_upd_per_frame": n_upd / n, "kernel_share_of_step": k4_ms / ms if ms > 0 else None,
+                "other_kernels_ms_per_step": {"pack": prof["pack"][0] / a.steps, "alloc": prof["alloc"][0] / a.steps}}
+
+    # ---- end to end through the C ABI with host buffers (rank-local copy of the sequence)
+    e2e = None
+    if not a.no_e2e:
+        hd = torch.empty(depth_dev.shape, dtype=depth_dev.dtype, pin_memory=True)
+        hc = torch.empty(rgb_dev.shape, dtype=rgb_dev.dtype, pin_memory=True)
+        hd.copy_(depth_dev); hc.copy_(rgb_dev)
+        torch.cuda.synchronize()
+
+        def e2e_step():
+            vol.reset()
+            vol.integrate_batch(hd, hc, seq.fxfycxcy, seq.extrinsic)
+            return vol.stats()            # D2H read of the step's result
+
+        with torch.cuda.stream(stream):
+            for _ in range(max(1, min(2, a.warmup))):
+                e2e_step()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(a.steps):
+                st = e2e_step()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        assert st["weight_sum"] == n_upd, "host-path result differs from the resident-path result"
+        t = torch.tensor([dt], dtype=torch.float64, device=f"cuda:{local}")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": n * a.steps / float(t.item()), "unit": UNIT,
+               "h2d_bytes_per_step": int(n * W * H * 5 + n * 16 * 8), "d2h_bytes_per_step": 16 + 16,
+               "api": "otslam_volume_reset + otslam_volume_integrate_batch(OTSLAM_MEM_HOST, pinned) + otslam_volume_stats"}
+
+    # ---- multi-GPU: extraction + NCCL gather of the extracted points (outside the timed region)
+    extra = {}
+    if world > 1:
+        from otslam_b200 import slab as slabmod
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        pts = slabmod.extract_and_gather_points(vol, rank, world, device=f"cuda:{local}")
+        torch.cuda.synchronize()
+        extra["extract_gather_ms"] = 1e3 * (time.perf_counter() - t0)
+        if rank == 0:
+            extra["gathered_points"] = int(pts[0].shape[0])
+
+    if rank == 0:
+        cpu = None
+        if not a.no_cpu and world == 1:
+            d, c = seq.numpy()
+            cpu, _, _ = cpu_sample(a, (d, c, seq.extrinsic, seq.fxfycxcy))
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload_name(a), "frames_per_step": n, "frames_per_launch": a.batch,
+                           "parallelism": "single GPU" if world == 1 else f"x-axis slabs of 8 blocks, cyclic over {world} ranks, +1 block halo",
+                           "l2": "inputs (%.0f MB) + volume (%.0f MB) exceed the 126 MB L2; no flush needed" % (
+                               n * W * H * 5 / 1e6, stats["n_blocks"] * 65536 / 1e6),
+                           "n_blocks": stats["n_blocks"]},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+                "clocks": clocks, "achieved_hbm_gbs_whole_step": bytes_step * a.steps / (ms_max * 1e-3) / 1e9}
+        line.update(extra)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.hd and a.voxel == 0.005:
+        a.voxel = 0.002
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -58,6 +58,12 @@ int otslam_volume_set_stream(otslam_volume* v, void* cuda_stream);
 /* frames fused per block residency in integrate_batch (1..32, default 32) */
 int otslam_volume_set_batch(otslam_volume* v, int frames_per_batch);
 
+/* kernel timing with CUDA events on the volume's stream (bench.py roofline): enable > 0 switches
+ * recording on and zeroes the accumulators, 0 switches it off, < 0 only reads; out_ms /
+ * out_launches (nullable, 4 entries: 0 = depth pack, 1 = block allocation, 2 = integration,
+ * 3 = reserved) return the totals accumulated before this call. */
+int otslam_volume_profile(otslam_volume* v, int enable, double* out_ms, int64_t* out_launches);
+
 /* ---- per-frame integration: RGBDImage.create_from_color_and_depth(depth_scale, depth_trunc,
  *      convert_rgb_to_intensity=False) + volume.integrate(rgbd, intrinsic, extrinsic)
  *      (3d_model/reconstruct_rgbd.py:99-107).  depth: H*W u16 (raw units), rgb: H*W*3 u8,

@@ -198,6 +198,12 @@ __global__ void __launch_bounds__(1024) scan_kernel(const int* __restrict__ in, 
     for (int i = b; i < e; ++i) { out[i] = acc; acc += in[i]; }
 }
 
+int device_exclusive_scan(const int* d_in, int64_t* d_out, int n, cudaStream_t s) {
+    scan_kernel<<<1, 1024, 0, s>>>(d_in, d_out, n);
+    OT_LAUNCHED();
+    return OTSLAM_OK;
+}
+
 __global__ void scatter_base_kernel(const int32_t* __restrict__ bslots, const int64_t* __restrict__ vbase, int n,
                                     int64_t* __restrict__ vbase_by_slot) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

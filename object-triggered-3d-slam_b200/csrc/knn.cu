@@ -1,0 +1,541 @@
+// knn.cu -- voxel_down_sample and statistical outlier removal on sm_100a.
+//
+//   voxel_down_sample          PointCloud.voxel_down_sample (/root/reference/3d_model/check_one_frame.py:28)
+//   remove_statistical_outlier PointCloud.remove_statistical_outlier (north_star)
+//
+// Both need "sum in point-index order" semantics to be bit-identical to the CPU algorithm, so the
+// points are bucketed with a STABLE radix sort (voxel / cell key, point index) and every bucket is
+// reduced sequentially.  The k-NN search is one warp per query over a hashed uniform grid: lanes
+// look up the cells of a ring in parallel, the warp scans their points cooperatively and keeps the
+// k best squared distances (exact FP64, the reference's (dx^2+dy^2)+dz^2 order) in shared memory.
+// The radix sort itself is cub::DeviceRadixSort (CUDA toolkit header library) -- plain plumbing.
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "volume.cuh"
+
+namespace otslam {
+
+int device_exclusive_scan(const int* d_in, int64_t* d_out, int n, cudaStream_t s);
+
+// ---- exact min / max of FP64 coordinates via order-preserving integer keys
+__device__ __forceinline__ unsigned long long d2key(double d) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(d);
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+static double key2d(unsigned long long k) {
+    const unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k;
+    double d;
+    memcpy(&d, &b, 8);
+    return d;
+}
+
+__global__ void __launch_bounds__(256) minmax_kernel(const double* __restrict__ pts, int64_t n, unsigned long long* mm /*[6]: min xyz, max xyz*/) {
+    unsigned long long lo[3] = {~0ull, ~0ull, ~0ull}, hi[3] = {0, 0, 0};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const unsigned long long k = d2key(pts[3 * i + a]);
+            lo[a] = min(lo[a], k);
+            hi[a] = max(hi[a], k);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        for (int o = 16; o; o >>= 1) {
+            lo[a] = min(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+            hi[a] = max(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicMin(mm + a, lo[a]);
+            atomicMax(mm + 3 + a, hi[a]);
+        }
+    }
+}
+
+static int cloud_minmax(const double* d_pts, int64_t n, double* mn, double* mx) {
+    DevBuf<unsigned long long> mm;
+    OT_CUDA(mm.alloc(6));
+    unsigned long long init[6] = {~0ull, ~0ull, ~0ull, 0, 0, 0};
+    OT_CUDA(cudaMemcpy(mm.p, init, sizeof(init), cudaMemcpyHostToDevice));
+    minmax_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 148 * 8), 256>>>(d_pts, n, mm.p);
+    OT_LAUNCHED();
+    unsigned long long h[6];
+    OT_CUDA(cudaMemcpy(h, mm.p, sizeof(h), cudaMemcpyDeviceToHost));
+    for (int a = 0; a < 3; ++a) { mn[a] = key2d(h[a]); mx[a] = key2d(h[3 + a]); }
+    return OTSLAM_OK;
+}
+
+// key = floor((p - origin) / cell) per axis, 21 bits each (the host checks the range)
+__global__ void __launch_bounds__(256) cell_key_kernel(const double* __restrict__ pts, int64_t n, double ox, double oy, double oz,
+                                                       double cell, int clamp_hi_x, int clamp_hi_y, int clamp_hi_z,
+                                                       uint64_t* __restrict__ keys, int32_t* __restrict__ idx) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int kx = (int)floor(__ddiv_rn(__dsub_rn(pts[3 * i], ox), cell));
+    int ky = (int)floor(__ddiv_rn(__dsub_rn(pts[3 * i + 1], oy), cell));
+    int kz = (int)floor(__ddiv_rn(__dsub_rn(pts[3 * i + 2], oz), cell));
+    if (clamp_hi_x >= 0) {   // k-NN grid: clamp into the grid (voxel_down_sample passes -1: exact keys)
+        kx = min(max(kx, 0), clamp_hi_x); ky = min(max(ky, 0), clamp_hi_y); kz = min(max(kz, 0), clamp_hi_z);
+    }
+    keys[i] = ((uint64_t)(uint32_t)kx << 42) | ((uint64_t)(uint32_t)ky << 21) | (uint64_t)(uint32_t)kz;
+    idx[i] = (int32_t)i;
+}
+
+static int sort_pairs(DevBuf<uint64_t>& k_in, DevBuf<int32_t>& v_in, DevBuf<uint64_t>& k_out, DevBuf<int32_t>& v_out, int64_t n) {
+    size_t tmp_bytes = 0;
+    OT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in.p, k_out.p, v_in.p, v_out.p, (int)n, 0, 63));
+    DevBuf<uint8_t> tmp;
+    OT_CUDA(tmp.alloc(tmp_bytes));
+    OT_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, k_in.p, k_out.p, v_in.p, v_out.p, (int)n, 0, 63));
+    g_launches.fetch_add(1);
+    return OTSLAM_OK;
+}
+
+// segment heads of the sorted keys: count pass / emit pass (ordered)
+__global__ void __launch_bounds__(256) seg_heads_kernel(const uint64_t* __restrict__ keys, int64_t n, const int64_t* __restrict__ base,
+                                                        int* __restrict__ counts, int32_t* __restrict__ seg_start) {
+    __shared__ int warp_sum[8];
+    const int64_t p0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
+    bool head[4];
+    int mine = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int64_t p = p0 + k;
+        head[k] = (p < n) && (p == 0 || keys[p] != keys[p - 1]);
+        mine += head[k];
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int inc = mine;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    if (lane == 31) warp_sum[wid] = inc;
+    __syncthreads();
+    int b = 0, tot = 0;
+    for (int w = 0; w < 8; ++w) { if (w < wid) b += warp_sum[w]; tot += warp_sum[w]; }
+    if (!base) {
+        if (threadIdx.x == 0) counts[blockIdx.x] = tot;
+        return;
+    }
+    int64_t o = base[blockIdx.x] + b + inc - mine;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (head[k]) seg_start[o++] = (int32_t)(p0 + k);
+}
+
+static int find_segments(const uint64_t* d_keys, int64_t n, DevBuf<int32_t>& seg_start, int64_t* n_seg) {
+    const int n_cta = (int)((n + 1023) / 1024);
+    DevBuf<int> counts;
+    DevBuf<int64_t> base;
+    OT_CUDA(counts.alloc(n_cta));
+    OT_CUDA(base.alloc(n_cta + 1));
+    seg_heads_kernel<<<n_cta, 256>>>(d_keys, n, nullptr, counts.p, nullptr);
+    OT_LAUNCHED();
+    OT_TRY(device_exclusive_scan(counts.p, base.p, n_cta, 0));
+    OT_CUDA(cudaMemcpy(n_seg, base.p + n_cta, 8, cudaMemcpyDeviceToHost));
+    OT_CUDA(seg_start.alloc(*n_seg + 1));
+    seg_heads_kernel<<<n_cta, 256>>>(d_keys, n, base.p, nullptr, seg_start.p);
+    OT_LAUNCHED();
+    const int32_t nn = (int32_t)n;
+    OT_CUDA(cudaMemcpy(seg_start.p + *n_seg, &nn, 4, cudaMemcpyHostToDevice));
+    return OTSLAM_OK;
+}
+
+// one thread per voxel: sequential FP64 sums in point-index order (stable sort => ascending indices)
+__global__ void __launch_bounds__(128) voxel_mean_kernel(const double* __restrict__ pts, const double* __restrict__ cols,
+                                                         const uint64_t* __restrict__ keys, const int32_t* __restrict__ idx,
+                                                         const int32_t* __restrict__ seg_start, int64_t n_seg,
+                                                         double* __restrict__ out_pts, double* __restrict__ out_cols,
+                                                         int32_t* __restrict__ out_keys, int32_t* __restrict__ out_counts) {
+    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n_seg) return;
+    const int b = seg_start[m], e = seg_start[m + 1];
+    double sp[3] = {0, 0, 0}, sc[3] = {0, 0, 0};
+    for (int j = b; j < e; ++j) {
+        const size_t i = (size_t)idx[j];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            sp[a] = __dadd_rn(sp[a], pts[3 * i + a]);
+            if (cols) sc[a] = __dadd_rn(sc[a], cols[3 * i + a]);
+        }
+    }
+    const double cnt = (double)(e - b);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        out_pts[3 * m + a] = __ddiv_rn(sp[a], cnt);
+        if (cols && out_cols) out_cols[3 * m + a] = __ddiv_rn(sc[a], cnt);
+    }
+    const uint64_t k = keys[b];
+    if (out_keys) {
+        out_keys[3 * m] = (int32_t)((k >> 42) & 0x1FFFFF);
+        out_keys[3 * m + 1] = (int32_t)((k >> 21) & 0x1FFFFF);
+        out_keys[3 * m + 2] = (int32_t)(k & 0x1FFFFF);
+    }
+    if (out_counts) out_counts[m] = e - b;
+}
+
+// ---- k-NN grid hash: cell key -> segment id
+__global__ void __launch_bounds__(256) cell_hash_build_kernel(const uint64_t* __restrict__ sorted_keys, const int32_t* __restrict__ seg_start,
+                                                              int64_t n_seg, uint64_t* hkeys, int32_t* hvals, uint32_t cap_mask) {
+    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n_seg) return;
+    const uint64_t key = sorted_keys[seg_start[m]];
+    uint32_t h = hash_key(key) & cap_mask;
+    for (;;) {
+        const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(hkeys + h), (unsigned long long)kEmptyKey,
+                                                 (unsigned long long)key);
+        if (old == (unsigned long long)kEmptyKey) { hvals[h] = (int32_t)m; return; }
+        h = (h + 1) & cap_mask;
+    }
+}
+
+struct KnnArgs {
+    const double* pts;          // original order
+    const int32_t* idx;         // sorted position -> original index
+    const int32_t* seg_start;   // [n_seg+1]
+    const uint64_t* hkeys;
+    const int32_t* hvals;
+    uint32_t cap_mask;
+    int64_t n;
+    int k;
+    double mn[3], cell;
+    int dim[3];
+    double* dbar;               // [n] original order
+};
+
+constexpr int kKnnWarps = 8;
+constexpr int kKnnMaxK = 128;
+
+__device__ __forceinline__ void warp_argmax(const double* best, int cnt, int lane, double& vmax, int& pmax) {
+    double v = -1.0;
+    int p = 0;
+    for (int e = lane; e < cnt; e += 32) {
+        const double b = best[e];
+        if (b > v) { v = b; p = e; }
+    }
+    for (int o = 16; o; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+        const int op = __shfl_xor_sync(0xffffffffu, p, o);
+        if (ov > v || (ov == v && op < p)) { v = ov; p = op; }
+    }
+    vmax = v; pmax = p;
+}
+
+__global__ void __launch_bounds__(kKnnWarps * 32) knn_mean_dist_kernel(KnnArgs a) {
+    __shared__ double s_best[kKnnWarps][kKnnMaxK];
+    __shared__ double s_sorted[kKnnWarps][kKnnMaxK];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t qpos = (int64_t)blockIdx.x * kKnnWarps + wid;
+    if (qpos >= a.n) return;
+    double* best = s_best[wid];
+    double* sorted = s_sorted[wid];
+    const int qi = a.idx[qpos];
+    const double q[3] = {a.pts[3 * (size_t)qi], a.pts[3 * (size_t)qi + 1], a.pts[3 * (size_t)qi + 2]};
+    int c[3];
+#pragma unroll
+    for (int ax = 0; ax < 3; ++ax) {
+        const int v = (int)floor(__ddiv_rn(__dsub_rn(q[ax], a.mn[ax]), a.cell));
+        c[ax] = min(max(v, 0), a.dim[ax] - 1);
+    }
+    const int k = a.k;
+    int found = 0;
+    double thr = 0.0;   // current k-th best (valid when found == k)
+    int pos = 0;
+    const int maxring = max(a.dim[0], max(a.dim[1], a.dim[2]));
+    for (int ring = 0; ring <= maxring; ++ring) {
+        if (found >= k && ring >= 1) {
+            // distance from q to the nearest face of the already scanned box that still has grid behind it
+            double reach = 1e300;
+#pragma unroll
+            for (int ax = 0; ax < 3; ++ax) {
+                if (c[ax] - (ring - 1) > 0) reach = fmin(reach, q[ax] - (a.mn[ax] + (double)(c[ax] - (ring - 1)) * a.cell));
+                if (c[ax] + ring < a.dim[ax]) reach = fmin(reach, (a.mn[ax] + (double)(c[ax] + ring) * a.cell) - q[ax]);
+            }
+            if (reach == 1e300) break;                 // the box covers the whole grid
+            reach -= 1e-9 * a.cell;                    // conservative against rounding of the cell boundaries
+            if (reach > 0.0 && reach * reach > thr) break;
+        }
+        // enumerate the shell cells of this ring, 32 at a time (one hash lookup per lane)
+        const int side = 2 * ring + 1;
+        const int ncell = ring == 0 ? 1 : side * side * side - (side - 2) * (side - 2) * (side - 2);
+        for (int c0 = 0; c0 < ncell; c0 += 32) {
+            const int ci = c0 + lane;
+            int seg = -1;
+            if (ci < ncell) {
+                int dx, dy, dz;
+                if (ring == 0) { dx = dy = dz = 0; }
+                else {
+                    // shell = two full z-caps (side*side each) + side walls: (side-2) z-layers of a square ring (4*side-4)
+                    const int cap = side * side;
+                    if (ci < 2 * cap) {
+                        const int w = ci % cap;
+                        dz = (ci < cap) ? -ring : ring;
+                        dx = w / side - ring; dy = w % side - ring;
+                    } else {
+                        const int r = ci - 2 * cap, per = 4 * side - 4;
+                        dz = r / per - ring + 1;
+                        const int w = r % per;
+                        if (w < side) { dx = -ring; dy = w - ring; }
+                        else if (w < 2 * side) { dx = ring; dy = w - side - ring; }
+                        else if (w < 3 * side - 2) { dy = -ring; dx = w - 2 * side - ring + 1; }
+                        else { dy = ring; dx = w - (3 * side - 2) - ring + 1; }
+                    }
+                }
+                const int x = c[0] + dx, y = c[1] + dy, z = c[2] + dz;
+                if (x >= 0 && x < a.dim[0] && y >= 0 && y < a.dim[1] && z >= 0 && z < a.dim[2]) {
+                    const uint64_t key = ((uint64_t)(uint32_t)x << 42) | ((uint64_t)(uint32_t)y << 21) | (uint64_t)(uint32_t)z;
+                    uint32_t h = hash_key(key) & a.cap_mask;
+                    for (;;) {
+                        const uint64_t hk = a.hkeys[h];
+                        if (hk == key) { seg = a.hvals[h]; break; }
+                        if (hk == kEmptyKey) break;
+                        h = (h + 1) & a.cap_mask;
+                    }
+                }
+            }
+            unsigned have = __ballot_sync(0xffffffffu, seg >= 0);
+            while (have) {
+                const int src = __ffs(have) - 1;
+                have &= have - 1;
+                const int sg = __shfl_sync(0xffffffffu, seg, src);
+                const int b = a.seg_start[sg], e = a.seg_start[sg + 1];
+                for (int j0 = b; j0 < e; j0 += 32) {
+                    const int j = j0 + lane;
+                    double d2 = 0.0;
+                    bool cand = false;
+                    if (j < e) {
+                        const size_t pi = (size_t)a.idx[j];
+                        const double dx = __dsub_rn(q[0], a.pts[3 * pi]), dy = __dsub_rn(q[1], a.pts[3 * pi + 1]),
+                                     dz = __dsub_rn(q[2], a.pts[3 * pi + 2]);
+                        d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                        cand = true;
+                    }
+                    unsigned todo = __ballot_sync(0xffffffffu, cand && (found < k || d2 < thr));
+                    while (todo) {
+                        const int L = __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        const double d = __shfl_sync(0xffffffffu, d2, L);
+                        if (found < k) {
+                            if (lane == 0) best[found] = d;
+                            ++found;
+                            __syncwarp();
+                            if (found == k) warp_argmax(best, k, lane, thr, pos);
+                        } else if (d < thr) {
+                            if (lane == 0) best[pos] = d;
+                            __syncwarp();
+                            warp_argmax(best, k, lane, thr, pos);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    __syncwarp();
+    // ascending order, then the sequential sum of square roots
+    for (int e = lane; e < found; e += 32) {
+        const double v = best[e];
+        int rank = 0;
+        for (int i = 0; i < found; ++i) {
+            const double o = best[i];
+            rank += (o < v) || (o == v && i < e);
+        }
+        sorted[rank] = v;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        double s = 0.0;
+        for (int j = 0; j < found; ++j) s = __dadd_rn(s, __dsqrt_rn(sorted[j]));
+        a.dbar[qi] = found > 0 ? __ddiv_rn(s, (double)found) : -1.0;
+    }
+}
+
+// sequential-order sum over n values with one warp (see cloud.cu: ordered_accumulate_kernel):
+//   mode 0: sum of (x > 0 ? x : 0)            mode 1: sum of (x > 0 ? (x-mean)^2 : 0)
+__global__ void __launch_bounds__(32) ordered_stat_kernel(const double* __restrict__ x, int64_t n, int mode, double mean,
+                                                          double* __restrict__ out) {
+    const int lane = threadIdx.x;
+    double acc = 0.0;
+    for (int64_t b = 0; b < n; b += 32) {
+        const int64_t i = b + lane;
+        double v = 0.0;
+        if (i < n) {
+            const double d = x[i];
+            if (d > 0.0) v = (mode == 0) ? d : __dmul_rn(__dsub_rn(d, mean), __dsub_rn(d, mean));
+        }
+        const int cnt = (int)min((int64_t)32, n - b);
+        for (int j = 0; j < cnt; ++j) acc = __dadd_rn(acc, __shfl_sync(0xffffffffu, v, j));
+    }
+    if (lane == 0) out[0] = acc;
+}
+
+__global__ void __launch_bounds__(256) sor_select_kernel(const double* __restrict__ dbar, int64_t n, double thr,
+                                                         const int64_t* __restrict__ base, int* __restrict__ counts,
+                                                         int64_t* __restrict__ out_idx) {
+    __shared__ int warp_sum[8];
+    const int64_t p0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
+    bool keep[4];
+    int mine = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int64_t p = p0 + k;
+        keep[k] = (p < n) && (dbar[p] > 0.0) && (dbar[p] < thr);
+        mine += keep[k];
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int inc = mine;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    if (lane == 31) warp_sum[wid] = inc;
+    __syncthreads();
+    int b = 0, tot = 0;
+    for (int w = 0; w < 8; ++w) { if (w < wid) b += warp_sum[w]; tot += warp_sum[w]; }
+    if (!base) {
+        if (threadIdx.x == 0) counts[blockIdx.x] = tot;
+        return;
+    }
+    int64_t o = base[blockIdx.x] + b + inc - mine;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (keep[k]) out_idx[o++] = p0 + k;
+}
+
+}  // namespace otslam
+
+using namespace otslam;
+
+extern "C" {
+
+int otslam_cloud_voxel_down_sample(const double* points, const double* colors, int64_t n, double voxel_size, double* out_points,
+                                   double* out_colors, int32_t* out_keys, int32_t* out_counts, int64_t* n_out, int device) {
+    if (!n_out || n < 0 || (n && !points)) return set_error(OTSLAM_ERR_INVALID, "bad arguments");
+    *n_out = 0;
+    if (!(voxel_size > 0.0)) return set_error(OTSLAM_ERR_INVALID, "[VoxelDownSample] voxel_size <= 0.");
+    if (n == 0) return OTSLAM_OK;
+    if (n > 0x7fffffffLL) return set_error(OTSLAM_ERR_OVERFLOW, "more than 2^31 points");
+    OT_TRY(use_device(device));
+    DevBuf<double> dp, dc;
+    OT_CUDA(dp.alloc(n * 3));
+    OT_CUDA(cudaMemcpy(dp.p, points, n * 24, cudaMemcpyHostToDevice));
+    if (colors) { OT_CUDA(dc.alloc(n * 3)); OT_CUDA(cudaMemcpy(dc.p, colors, n * 24, cudaMemcpyHostToDevice)); }
+    double mn[3], mx[3];
+    OT_TRY(cloud_minmax(dp.p, n, mn, mx));
+    double vmin[3];
+    for (int a = 0; a < 3; ++a) {
+        vmin[a] = mn[a] - voxel_size * 0.5;
+        const double vmax = mx[a] + voxel_size * 0.5;
+        if (voxel_size * 2147483647.0 < vmax - vmin[a]) return set_error(OTSLAM_ERR_INVALID, "[VoxelDownSample] voxel_size is too small.");
+        if (std::floor((mx[a] - vmin[a]) / voxel_size) >= 2097152.0)
+            return set_error(OTSLAM_ERR_OVERFLOW, "[VoxelDownSample] more than 2^21 voxels along one axis is not supported on the GPU path");
+    }
+    DevBuf<uint64_t> k0, k1;
+    DevBuf<int32_t> i0, i1;
+    OT_CUDA(k0.alloc(n)); OT_CUDA(k1.alloc(n)); OT_CUDA(i0.alloc(n)); OT_CUDA(i1.alloc(n));
+    cell_key_kernel<<<(unsigned)((n + 255) / 256), 256>>>(dp.p, n, vmin[0], vmin[1], vmin[2], voxel_size, -1, -1, -1, k0.p, i0.p);
+    OT_LAUNCHED();
+    OT_TRY(sort_pairs(k0, i0, k1, i1, n));
+    DevBuf<int32_t> seg;
+    int64_t m = 0;
+    OT_TRY(find_segments(k1.p, n, seg, &m));
+    *n_out = m;
+    if (!out_points) return OTSLAM_OK;
+    DevBuf<double> op, oc;
+    DevBuf<int32_t> ok, on;
+    OT_CUDA(op.alloc(m * 3)); OT_CUDA(oc.alloc(m * 3)); OT_CUDA(ok.alloc(m * 3)); OT_CUDA(on.alloc(m));
+    voxel_mean_kernel<<<(unsigned)((m + 127) / 128), 128>>>(dp.p, colors ? dc.p : nullptr, k1.p, i1.p, seg.p, m, op.p, oc.p, ok.p, on.p);
+    OT_LAUNCHED();
+    OT_CUDA(cudaMemcpy(out_points, op.p, m * 24, cudaMemcpyDeviceToHost));
+    if (colors && out_colors) OT_CUDA(cudaMemcpy(out_colors, oc.p, m * 24, cudaMemcpyDeviceToHost));
+    if (out_keys) OT_CUDA(cudaMemcpy(out_keys, ok.p, m * 12, cudaMemcpyDeviceToHost));
+    if (out_counts) OT_CUDA(cudaMemcpy(out_counts, on.p, m * 4, cudaMemcpyDeviceToHost));
+    return OTSLAM_OK;
+}
+
+int otslam_cloud_remove_statistical_outlier(const double* points, int64_t n, int nb_neighbors, double std_ratio,
+                                            int64_t* out_indices, int64_t* n_out, double* mean_dist, int device) {
+    if (!n_out || n < 0 || (n && (!points || !out_indices))) return set_error(OTSLAM_ERR_INVALID, "bad arguments");
+    *n_out = 0;
+    if (nb_neighbors < 1 || !(std_ratio > 0.0))
+        return set_error(OTSLAM_ERR_INVALID, "[RemoveStatisticalOutliers] Illegal input parameters, the number of neighbors and "
+                                             "standard deviation ratio must be positive.");
+    if (n == 0) return OTSLAM_OK;
+    if (n > 0x7fffffffLL) return set_error(OTSLAM_ERR_OVERFLOW, "more than 2^31 points");
+    const int k = (int)std::min<int64_t>(nb_neighbors, n);
+    if (k > kKnnMaxK) return set_error(OTSLAM_ERR_INVALID, "nb_neighbors > 128 is not supported on the GPU path");
+    OT_TRY(use_device(device));
+    DevBuf<double> dp;
+    OT_CUDA(dp.alloc(n * 3));
+    OT_CUDA(cudaMemcpy(dp.p, points, n * 24, cudaMemcpyHostToDevice));
+    KnnArgs a;
+    double mx[3];
+    OT_TRY(cloud_minmax(dp.p, n, a.mn, mx));
+    // uniform grid: ~2 points per cell of the bounding box volume, at most 1024 cells per axis
+    const double ext[3] = {mx[0] - a.mn[0], mx[1] - a.mn[1], mx[2] - a.mn[2]};
+    const double vol = std::max(ext[0], 1e-9) * std::max(ext[1], 1e-9) * std::max(ext[2], 1e-9);
+    double cell = std::cbrt(vol / std::max(1.0, (double)n / 2.0));
+    const double maxext = std::max(ext[0], std::max(ext[1], ext[2]));
+    cell = std::max(cell, maxext / 1024.0);
+    if (!(cell > 0.0) || !std::isfinite(cell)) cell = 1.0;
+    a.cell = cell;
+    for (int ax = 0; ax < 3; ++ax) a.dim[ax] = std::max(1, (int)std::floor(ext[ax] / cell) + 1);
+    DevBuf<uint64_t> k0, k1;
+    DevBuf<int32_t> i0, i1;
+    OT_CUDA(k0.alloc(n)); OT_CUDA(k1.alloc(n)); OT_CUDA(i0.alloc(n)); OT_CUDA(i1.alloc(n));
+    cell_key_kernel<<<(unsigned)((n + 255) / 256), 256>>>(dp.p, n, a.mn[0], a.mn[1], a.mn[2], cell, a.dim[0] - 1, a.dim[1] - 1,
+                                                         a.dim[2] - 1, k0.p, i0.p);
+    OT_LAUNCHED();
+    OT_TRY(sort_pairs(k0, i0, k1, i1, n));
+    DevBuf<int32_t> seg;
+    int64_t n_seg = 0;
+    OT_TRY(find_segments(k1.p, n, seg, &n_seg));
+    uint32_t cap = 1024;
+    while ((int64_t)cap < 2 * n_seg) cap <<= 1;
+    DevBuf<uint64_t> hk;
+    DevBuf<int32_t> hv;
+    OT_CUDA(hk.alloc(cap)); OT_CUDA(hv.alloc(cap));
+    OT_CUDA(cudaMemset(hk.p, 0xFF, (size_t)cap * 8));
+    cell_hash_build_kernel<<<(unsigned)((n_seg + 255) / 256), 256>>>(k1.p, seg.p, n_seg, hk.p, hv.p, cap - 1);
+    OT_LAUNCHED();
+    DevBuf<double> dbar, scal;
+    OT_CUDA(dbar.alloc(n)); OT_CUDA(scal.alloc(1));
+    a.pts = dp.p; a.idx = i1.p; a.seg_start = seg.p; a.hkeys = hk.p; a.hvals = hv.p; a.cap_mask = cap - 1; a.n = n; a.k = k; a.dbar = dbar.p;
+    knn_mean_dist_kernel<<<(unsigned)((n + kKnnWarps - 1) / kKnnWarps), kKnnWarps * 32>>>(a);
+    OT_LAUNCHED();
+    if (mean_dist) OT_CUDA(cudaMemcpy(mean_dist, dbar.p, n * 8, cudaMemcpyDeviceToHost));
+    // global statistics in sequential index order; scalars finished on the host in FP64
+    double sum = 0.0, sq = 0.0;
+    ordered_stat_kernel<<<1, 32>>>(dbar.p, n, 0, 0.0, scal.p);
+    OT_LAUNCHED();
+    OT_CUDA(cudaMemcpy(&sum, scal.p, 8, cudaMemcpyDeviceToHost));
+    const int64_t valid = n;   // the query point is its own first neighbour, so every point has >= 1
+    const double mean = sum / (double)valid;
+    ordered_stat_kernel<<<1, 32>>>(dbar.p, n, 1, mean, scal.p);
+    OT_LAUNCHED();
+    OT_CUDA(cudaMemcpy(&sq, scal.p, 8, cudaMemcpyDeviceToHost));
+    const double sd = valid > 1 ? std::sqrt(sq / (double)(valid - 1)) : 0.0;
+    const double thr = mean + std_ratio * sd;
+    const int n_cta = (int)((n + 1023) / 1024);
+    DevBuf<int> counts;
+    DevBuf<int64_t> base, oidx;
+    OT_CUDA(counts.alloc(n_cta)); OT_CUDA(base.alloc(n_cta + 1));
+    sor_select_kernel<<<n_cta, 256>>>(dbar.p, n, thr, nullptr, counts.p, nullptr);
+    OT_LAUNCHED();
+    OT_TRY(device_exclusive_scan(counts.p, base.p, n_cta, 0));
+    int64_t m = 0;
+    OT_CUDA(cudaMemcpy(&m, base.p + n_cta, 8, cudaMemcpyDeviceToHost));
+    *n_out = m;
+    if (m == 0) return OTSLAM_OK;
+    OT_CUDA(oidx.alloc(m));
+    sor_select_kernel<<<n_cta, 256>>>(dbar.p, n, thr, base.p, nullptr, oidx.p);
+    OT_LAUNCHED();
+    OT_CUDA(cudaMemcpy(out_indices, oidx.p, m * 8, cudaMemcpyDeviceToHost));
+    return OTSLAM_OK;
+}
+
+}  // extern "C"

@@ -79,6 +79,14 @@ struct otslam_volume {
     int mult_w = 0, mult_h = 0;
     double mult_intr[4] = {0, 0, 0, 0};
 
+    // optional per-kernel timing (otslam_volume_profile)
+    bool profiling = false;
+    double prof_ms[4] = {0, 0, 0, 0};
+    int64_t prof_launches[4] = {0, 0, 0, 0};
+    std::vector<cudaEvent_t> prof_events;          // pairs, recycled
+    std::vector<int> prof_pending;                 // kernel id per recorded pair
+    size_t prof_used = 0;
+
     otslam::MeshResult mesh;
     otslam::PointsResult points;
 };

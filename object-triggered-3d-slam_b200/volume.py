@@ -37,6 +37,15 @@ class TSDFVolume:
     def set_batch(self, n):
         _lib.check(_lib.lib.otslam_volume_set_batch(self._h, int(n)))
 
+    def profile(self, enable=None):
+        """Per-kernel CUDA-event totals {pack, alloc, integrate}: (ms, launches) accumulated so far.
+        enable=True (re)starts recording from zero, False stops it, None only reads."""
+        ms = np.zeros(4, np.float64)
+        ln = np.zeros(4, np.int64)
+        _lib.check(_lib.lib.otslam_volume_profile(self._h, -1 if enable is None else int(bool(enable)), _lib.ptr(ms), _lib.ptr(ln)))
+        names = ("pack", "alloc", "integrate")
+        return {k: (float(ms[i]), int(ln[i])) for i, k in enumerate(names)}
+
     @staticmethod
     def _intr(intr):
         return np.ascontiguousarray(intr, np.float64).reshape(4)
