@@ -1,0 +1,65 @@
+"""Shared frame loop of the drop-in scripts.
+
+The reference integrates frame by frame (/root/reference/3d_model/reconstruct_rgbd.py:86-109:
+read colour, read depth, loadtxt pose, pose @ T_fix, inv, create_from_color_and_depth, integrate).
+Here the files are decoded on the host in chunks and each chunk goes to the GPU in ONE
+`integrate_sequence` call (frame order preserved, up to 32 frames fused per block residency);
+per-frame failures keep the reference's semantics: abort (reconstruct_rgbd.py, no try) or
+print-and-skip (reconstruct_rgbd_filter.py:108-109, multi_reconstruct_rgbd_filter.py:102-103).
+"""
+import sys
+
+import numpy as np
+
+from .o3d_compat import io as o3d_io
+
+CHUNK_FRAMES = 256
+_FMT = "[ScalableTSDFVolume::Integrate] Unsupported image format."
+
+
+def load_frame(color_path, depth_path, pose_path, intrinsics, T_fix):
+    """Decode one capture triple; returns (rgb u8 HxWx3, depth u16 HxW, extrinsic 4x4) or raises the
+    exception the reference's per-frame body would have raised."""
+    color = np.asarray(o3d_io.read_image(color_path))
+    depth = np.asarray(o3d_io.read_image(depth_path))
+    pose_ros = np.loadtxt(pose_path)
+    pose_optical = pose_ros @ T_fix
+    extrinsic = np.linalg.inv(pose_optical)
+    if color.size == 0 or depth.size == 0 or color.shape[:2] != depth.shape[:2]:
+        raise RuntimeError("[CreateFromColorAndDepth] Unsupported image format.")
+    if depth.ndim != 2 or depth.dtype != np.uint16 or color.ndim != 3 or color.shape[2] != 3 or color.dtype != np.uint8 \
+            or depth.shape != (intrinsics.height, intrinsics.width):
+        raise RuntimeError(_FMT)
+    return color, depth, extrinsic
+
+
+def integrate_files(volume, triples, intrinsics, T_fix, depth_scale=1000.0, depth_trunc=3.0, skip_errors=False,
+                    progress=None, on_error=None):
+    """Integrate capture triples [(color, depth, pose, label)] in order. Returns frames integrated."""
+    done = 0
+    n = len(triples)
+    for c0 in range(0, n, CHUNK_FRAMES):
+        cols, deps, exts = [], [], []
+        for k, (cp, dp, pp, label) in enumerate(triples[c0:c0 + CHUNK_FRAMES]):
+            try:
+                c, d, e = load_frame(cp, dp, pp, intrinsics, T_fix)
+            except Exception as err:  # noqa: BLE001
+                if not skip_errors:
+                    raise
+                if on_error:
+                    on_error(label, err)
+                continue
+            cols.append(c); deps.append(d); exts.append(e)
+            if progress:
+                progress(label, c0 + k + 1, n)
+        if exts:
+            volume.integrate_sequence(np.stack(deps), np.stack(cols), intrinsics, np.stack(exts), depth_scale, depth_trunc)
+            done += len(exts)
+    return done
+
+
+def stdout_progress(fmt):
+    def cb(label, i, n):
+        sys.stdout.write(fmt.format(label=label, i=i, n=n))
+        sys.stdout.flush()
+    return cb

@@ -1,0 +1,177 @@
+"""GPU parity for extraction (K5-K7) and the cloud operators (K1b, K8-K13) vs the oracle.
+Integer / index outputs bit-exact; FP64 outputs are produced with the oracle's operation order and
+are expected bit-exact too (chamfer <= 0.25 voxel is the contract's outer bound)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+from scipy.spatial import cKDTree
+
+from conftest import canon_mesh, lexorder
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def build_pair(seq, d, c, vl, slab=None):
+    from otslam_b200.volume import TSDFVolume
+    ov = oracle.Volume(vl, 4 * vl, slab=slab)
+    for k in range(len(seq)):
+        ov.integrate(oracle.depth_convert(d[k]), c[k], seq.fxfycxcy, seq.extrinsic[k])
+    gv = TSDFVolume(vl, 4 * vl, slab=slab)
+    gv.integrate_batch(d, c, seq.fxfycxcy, seq.extrinsic)
+    return gv, ov
+
+
+@pytest.mark.parametrize("slab", [None, (0, 2, 2, 0), (0, 2, 2, 1), (1, 1, 3, 2)])
+def test_mesh_and_points_parity(table_seq, slab):
+    seq, d, c = table_seq
+    vl = 0.01
+    gv, ov = build_pair(seq, d, c, vl, slab)
+    gverts, gcols, gnrm, gfaces, gek = gv.extract_triangle_mesh()
+    overts, ocols, ofaces, oek = ov.extract_triangle_mesh()
+    assert len(gverts) == len(overts) > 1000 and len(gfaces) == len(ofaces)
+    A, B = canon_mesh(overts, ocols, ofaces, oek), canon_mesh(gverts, gcols, gfaces, gek)
+    assert (A[3] == B[3]).all()                                  # same lattice edges
+    assert (A[0] == B[0]).all()                                  # vertex positions bit-exact (<< 0.25 voxel)
+    assert np.abs(A[1] - B[1]).max() <= 1e-9                     # colours (integer sums vs FP64 running mean)
+    assert (A[2] == B[2]).all()                                  # same triangles, same winding
+    d1 = cKDTree(overts).query(gverts)[0].mean() + cKDTree(gverts).query(overts)[0].mean()
+    assert d1 <= 0.25 * vl
+    assert np.abs(oracle.vertex_normals(gverts, gfaces) - gnrm).max() < 1e-9
+    gp, gc, gpe = gv.extract_point_cloud()
+    op, oc, ope = ov.extract_point_cloud()
+    a, b = lexorder(ope), lexorder(gpe)
+    assert len(gp) == len(op) and (ope[a] == gpe[b]).all() and (op[a] == gp[b]).all() and np.abs(oc[a] - gc[b]).max() <= 1e-9
+    gv.close()
+
+
+def test_slab_union_equals_full_volume(table_seq):
+    from otslam_b200 import slab as slabmod
+    seq, d, c = table_seq
+    full, _ = build_pair(seq, d, c, 0.01)
+    parts = [build_pair(seq, d, c, 0.01, slab=(0, 4, 3, r))[0] for r in range(3)]
+    fv = full.extract_triangle_mesh(normals=False)
+    merged = slabmod.merge_mesh_parts([(p[0], p[1], p[3], p[4]) for p in (v.extract_triangle_mesh(normals=False) for v in parts)])
+    A, B = canon_mesh(fv[0], fv[1], fv[3], fv[4]), canon_mesh(*merged)
+    assert (A[3] == B[3]).all() and (A[0] == B[0]).all() and (A[2] == B[2]).all()
+    fk = {tuple(k) for k in full.export_blocks(color=False)[0].tolist()}
+    pk = set()
+    for v in parts:
+        pk |= {tuple(k) for k in v.export_blocks(color=False)[0].tolist()}
+    assert pk == fk
+    for v in parts + [full]:
+        v.close()
+
+
+def test_empty_volume_extraction():
+    from otslam_b200.volume import TSDFVolume
+    v = TSDFVolume(0.01, 0.04)
+    verts, cols, nrm, faces, ek = v.extract_triangle_mesh()
+    assert len(verts) == 0 and len(faces) == 0
+    assert len(v.extract_point_cloud()[0]) == 0
+    v.close()
+
+
+@pytest.fixture(scope="module")
+def mesh(table_seq):
+    seq, d, c = table_seq
+    ov = oracle.Volume(0.01, 0.04)
+    for k in range(3):
+        ov.integrate(oracle.depth_convert(d[k]), c[k], seq.fxfycxcy, seq.extrinsic[k])
+    v, col, f, ek = ov.extract_triangle_mesh()
+    return v, col, f, oracle.vertex_normals(v, f)
+
+
+def test_backproject_and_depth_convert(table_seq):
+    import otslam_b200.o3d_compat as o3d
+    seq, d, c = table_seq
+    rgbd = o3d.geometry.RGBDImage.create_from_color_and_depth(o3d.geometry.Image(c[0]), o3d.geometry.Image(d[0]), 1000.0, 5.0, False)
+    intr = o3d.camera.PinholeCameraIntrinsic(640, 480, *seq.fxfycxcy)
+    for ext in (None, seq.extrinsic[0]):
+        pc = o3d.geometry.PointCloud.create_from_rgbd_image(rgbd, intr) if ext is None else \
+            o3d.geometry.PointCloud.create_from_rgbd_image(rgbd, intr, ext)
+        op, oc = oracle.backproject_rgbd(oracle.depth_convert(d[0], 1000.0, 5.0), c[0], seq.fxfycxcy, ext)
+        assert len(pc.points) == len(op) and (pc.points == op).all() and (pc.colors == oc).all()
+
+
+def test_vertex_normals_and_sampling(mesh):
+    import otslam_b200.o3d_compat as o3d
+    v, col, f, n = mesh
+    m = o3d.geometry.TriangleMesh()
+    m.vertices, m.vertex_colors, m.triangles = v, col, f
+    m.compute_vertex_normals()
+    assert np.abs(m.vertex_normals - n).max() < 1e-9
+    m.vertex_normals = n
+    pc = m.sample_points_uniformly(number_of_points=100000, seed=11)
+    op, oc, on, tri = oracle.sample_uniform(v, col, n, f, 100000, seed=11)
+    assert (pc.points == op).all() and (pc.colors == oc).all() and (pc.normals == on).all()   # same counter RNG -> point by point
+    pc2 = m.sample_points_uniformly(number_of_points=100000, seed=12)
+    assert not (pc2.points == op).all()
+    d2 = cKDTree(op).query(pc2.points)[0].mean() + cKDTree(pc2.points).query(op)[0].mean()
+    assert d2 <= 0.25 * 0.01 * 2 * 4                              # different seeds: same surface
+    with pytest.raises(RuntimeError):
+        o3d.geometry.TriangleMesh().sample_points_uniformly(10)
+    with pytest.raises(RuntimeError):
+        m.sample_points_uniformly(0)
+
+
+def test_zfilter_vds_sor(mesh):
+    import otslam_b200.o3d_compat as o3d
+    from otslam_b200 import _lib
+    v, col, f, n = mesh
+    pts, cols, _, _ = oracle.sample_uniform(v, col, None, f, 60000, seed=1)
+    zp, zc = oracle.zfilter(pts, cols, 0.03)
+    gp, gc, m = np.empty_like(pts), np.empty_like(cols), C.c_int64(0)
+    _lib.check(_lib.lib.otslam_cloud_zfilter(_lib.ptr(pts), _lib.ptr(cols), len(pts), 0.03, _lib.ptr(gp), _lib.ptr(gc), C.byref(m), 0))
+    assert m.value == len(zp) and (gp[:m.value] == zp).all() and (gc[:m.value] == zc).all()
+    pc = o3d.geometry.PointCloud(); pc.points, pc.colors = zp, zc
+    for vs in (0.01, 0.037):
+        ds = pc.voxel_down_sample(vs)
+        op, oc, ok, on = oracle.voxel_down_sample(zp, zc, vs)
+        assert len(ds.points) == len(op) and (ds.points == op).all() and (ds.colors == oc).all()
+    gk = np.empty((len(zp), 3), np.int32); gn = np.empty(len(zp), np.int32)
+    _lib.check(_lib.lib.otslam_cloud_voxel_down_sample(_lib.ptr(zp), None, len(zp), 0.037, _lib.ptr(gp), None, _lib.ptr(gk), _lib.ptr(gn), C.byref(m), 0))
+    assert (gk[:m.value] == ok).all() and (gn[:m.value] == on).all()            # voxel keys and counts bit-exact
+    rng = np.random.default_rng(0)
+    noisy = zp.copy()
+    noisy[::61] += rng.normal(0, 0.08, noisy[::61].shape)
+    noisy[10] = noisy[11]                                                        # duplicate point
+    for k, ratio in ((20, 2.0), (8, 1.0), (100, 2.5)):
+        sel, idx = (lambda r: (r[0], np.array(r[1])))(o3d.geometry.PointCloud(noisy).remove_statistical_outlier(k, ratio))
+        oi, odb = oracle.remove_statistical_outlier(noisy, k, ratio)
+        assert len(idx) == len(oi) and (idx == oi).all()                         # kept indices bit-exact
+        assert (sel.points == noisy[oi]).all()
+    with pytest.raises(RuntimeError):
+        o3d.geometry.PointCloud(noisy).remove_statistical_outlier(0, 1.0)
+    with pytest.raises(RuntimeError):
+        pc.voxel_down_sample(0.0)
+    tiny = o3d.geometry.PointCloud(noisy[:5])
+    sel, idx = tiny.remove_statistical_outlier(20, 2.0)                          # fewer points than neighbours
+    assert idx == oracle.remove_statistical_outlier(noisy[:5], 20, 2.0)[0].tolist()
+
+
+def test_grid_points_and_merge_pack(tmp_path):
+    import otslam_b200.o3d_compat as o3d
+    from otslam_b200 import _lib, synth
+    img = synth.occupancy_map(701, 533, 0.02, 3)
+    og = oracle.grid_to_points(img, 0.05, -17.3, -13.1, 100)
+    gg, m = np.empty((img.size, 3)), C.c_int64(0)
+    _lib.check(_lib.lib.otslam_grid_to_points(_lib.ptr(img), 701, 533, 0.05, -17.3, -13.1, 100, _lib.ptr(gg), C.byref(m), 0))
+    assert m.value == len(og) and (gg[:m.value] == og).all()
+    rng = np.random.default_rng(4)
+    clouds = [og, rng.normal(size=(1000, 3)), rng.normal(size=(777, 3)), np.zeros((0, 3))]
+    paint = [[0.2, 0.2, 0.2], [1, 0, 0], [1, 0, 0], [0, 1, 0]]
+    rec = o3d.io.pack_cloud_records(clouds, paint=paint)
+    ref = np.concatenate([oracle.pack_ply_cloud(c, np.tile(p, (len(c), 1))) for c, p in zip(clouds, paint)])
+    assert rec.shape == ref.shape and (rec == ref).all()                         # PLY bytes identical
+    cols = [rng.random((len(c), 3)) * 1.2 - 0.1 for c in clouds]                 # includes out-of-range colours (clamped)
+    rec2 = o3d.io.pack_cloud_records(clouds, colors_list=cols)
+    ref2 = np.concatenate([oracle.pack_ply_cloud(c, k) for c, k in zip(clouds, cols)])
+    assert (rec2 == ref2).all()
+    pc = o3d.geometry.PointCloud(); pc.points = clouds[1]; pc.colors = np.clip(cols[1], 0, 1)
+    p = str(tmp_path / "x.ply")
+    o3d.io.write_point_cloud(p, pc)
+    back = o3d.io.read_point_cloud(p)
+    assert (back.points == pc.points).all() and np.abs(back.colors - pc.colors).max() <= 0.5 / 255 + 1e-12
+    assert len(open(p, "rb").read().split(b"end_header\n", 1)[1]) == 27 * 1000

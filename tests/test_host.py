@@ -1,0 +1,174 @@
+"""Host-side logic that needs no GPU: the o3d_compat containers, PLY I/O layout,
+dataset discovery of the drop-in scripts, capture-tree writer, and the per-frame error semantics."""
+import importlib
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+import otslam_b200.o3d_compat as o3d
+from otslam_b200 import pipeline, synth
+
+
+def test_vector_containers_copy_in_and_view_out():
+    a = np.random.rand(5, 3)
+    pc = o3d.geometry.PointCloud()
+    pc.points = o3d.utility.Vector3dVector(a)
+    a[0, 0] = 99.0
+    assert pc.points[0, 0] != 99.0                       # copied in
+    assert np.asarray(pc.points) is pc.points            # view out
+    assert len(pc.points) == 5 and not pc.has_colors()
+    with pytest.raises(RuntimeError):
+        o3d.utility.Vector3dVector(np.zeros((3, 2)))
+
+
+def test_pointcloud_paint_and_concat_rules():
+    """colours survive += only if both sides have them."""
+    a = o3d.geometry.PointCloud(); a.points = np.random.rand(4, 3); a.paint_uniform_color([0.2, 0.2, 0.2])
+    b = o3d.geometry.PointCloud(); b.points = np.random.rand(3, 3); b.paint_uniform_color([1, 0, 0])
+    c = a + b
+    assert len(c.points) == 7 and c.has_colors() and (c.colors[:4] == 0.2).all() and (c.colors[4:] == [1, 0, 0]).all()
+    assert len(a.points) == 4                            # + does not modify its operands
+    d = o3d.geometry.PointCloud(); d.points = np.random.rand(2, 3)
+    e = a + d
+    assert len(e.points) == 6 and not e.has_colors()
+    empty = o3d.geometry.PointCloud()
+    empty += b
+    assert empty.has_colors() and len(empty.points) == 3
+    b.normals = np.random.rand(3, 3)
+    f = a + b
+    assert not f.has_normals()                            # the map has no normals -> dropped (hybrid_map.py:115)
+
+
+def test_ply_layouts(tmp_path):
+    """Open3D binary PLY: 27 B/point clouds need the GPU packer; normals+colours (51 B) and meshes
+    (51 B/vertex + 13 B/face) are host-packed here."""
+    pc = o3d.geometry.PointCloud()
+    pc.points = np.random.rand(10, 3); pc.normals = np.random.rand(10, 3); pc.colors = np.random.rand(10, 3)
+    p = str(tmp_path / "c.ply")
+    assert o3d.io.write_point_cloud(p, pc)
+    raw = open(p, "rb").read()
+    hdr = raw[:raw.index(b"end_header\n") + 11]
+    assert hdr.startswith(b"ply\nformat binary_little_endian 1.0\ncomment Created by Open3D\nelement vertex 10\nproperty double x")
+    assert len(raw) - len(hdr) == 10 * 51
+    q = o3d.io.read_point_cloud(p)
+    assert (q.points == pc.points).all() and (q.normals == pc.normals).all()
+    assert np.abs(q.colors - pc.colors).max() <= 0.5 / 255 + 1e-12
+    m = o3d.geometry.TriangleMesh()
+    m.vertices = np.random.rand(4, 3); m.vertex_normals = np.random.rand(4, 3); m.vertex_colors = np.random.rand(4, 3)
+    m.triangles = np.array([[0, 1, 2], [1, 3, 2]])
+    p2 = str(tmp_path / "m.ply")
+    assert o3d.io.write_triangle_mesh(p2, m)
+    raw = open(p2, "rb").read()
+    hdr = raw[:raw.index(b"end_header\n") + 11]
+    assert b"element face 2\nproperty list uchar uint vertex_indices\n" in hdr
+    assert len(raw) - len(hdr) == 4 * 51 + 2 * 13
+    r = o3d.io.read_triangle_mesh(p2)
+    assert (r.vertices == m.vertices).all() and (r.triangles == m.triangles).all() and r.has_vertex_normals()
+    as_cloud = o3d.io.read_point_cloud(p2)               # a mesh PLY read as a cloud yields its vertices
+    assert len(as_cloud.points) == 4
+    assert not o3d.io.write_point_cloud(str(tmp_path / "e.ply"), o3d.geometry.PointCloud())
+    assert len(o3d.io.read_point_cloud(str(tmp_path / "missing.ply")).points) == 0
+
+
+def test_read_ascii_ply(tmp_path):
+    p = tmp_path / "a.ply"
+    p.write_text("ply\nformat ascii 1.0\nelement vertex 2\nproperty float x\nproperty float y\nproperty float z\n"
+                 "property uchar red\nproperty uchar green\nproperty uchar blue\nend_header\n0 0 0 255 0 0\n1 2 3 0 255 0\n")
+    pc = o3d.io.read_point_cloud(str(p))
+    assert (pc.points == [[0, 0, 0], [1, 2, 3]]).all() and (pc.colors == [[1, 0, 0], [0, 1, 0]]).all()
+
+
+def test_missing_image_is_empty_not_exception(tmp_path, capsys):
+    img = o3d.io.read_image(str(tmp_path / "nope.png"))
+    assert img.is_empty() and "Read image failed" in capsys.readouterr().out
+    with pytest.raises(RuntimeError):
+        o3d.geometry.RGBDImage.create_from_color_and_depth(img, img, convert_rgb_to_intensity=False)
+
+
+def test_capture_tree_and_discovery(tmp_path, monkeypatch):
+    intr = (64, 48, 56.0, 56.0, 32.5, 24.5)
+    seq = synth.make_sequence("table", 12, intr=intr)
+    base = str(tmp_path / "scan")
+    synth.write_capture_tree(seq, base, label="Object_0")
+    synth.write_capture_tree(seq, base, label="Object_1", start=1)
+    assert sorted(os.listdir(os.path.join(base, "depth")))[0] == "Object_0_1.png"
+    txt = open(os.path.join(base, "poses", "Object_0_1.txt")).read().split("\n")
+    assert len(txt[0].split()) == 4 and txt[3].split() == ["0.000000", "0.000000", "0.000000", "1.000000"]
+    monkeypatch.setenv("OTSLAM_BASE_DIR", base)
+    sys.path.insert(0, os.path.join(ROOT, "3d_model"))
+    for name in ("_common", "reconstruct_rgbd"):
+        sys.modules.pop(name, None)
+    mod = importlib.import_module("reconstruct_rgbd")
+    try:
+        assert mod.get_unique_object_names() == ["Object_0", "Object_1"]
+        tr = mod.frame_triples("Object_0")
+        # lexicographic order: _10 sorts before _2, identically for the three lists
+        assert [os.path.basename(t[0]) for t in tr][:4] == ["Object_0_1.jpg", "Object_0_10.jpg", "Object_0_11.jpg", "Object_0_12.jpg"]
+        assert all(os.path.basename(t[0])[:-4] == os.path.basename(t[1])[:-4] == os.path.basename(t[2])[:-4] for t in tr)
+        assert os.path.isdir(os.path.join(base, "3d_reconst"))      # created at import like the reference
+        assert (mod.T_fix == synth.T_FIX).all() and mod.intrinsics.width == 640
+        assert (mod.VOXEL_LENGTH, mod.SDF_TRUNC) == (0.01, 0.04)    # reference defaults
+    finally:
+        sys.path.remove(os.path.join(ROOT, "3d_model"))
+        for name in ("_common", "reconstruct_rgbd"):
+            sys.modules.pop(name, None)
+
+
+def test_load_frame_errors_follow_reference_semantics(tmp_path):
+    intr = o3d.camera.PinholeCameraIntrinsic(64, 48, 56.0, 56.0, 32.5, 24.5)
+    seq = synth.make_sequence("table", 3, intr=(64, 48, 56.0, 56.0, 32.5, 24.5))
+    base = str(tmp_path / "scan")
+    synth.write_capture_tree(seq, base)
+    ok = [os.path.join(base, s, f"Object_0_1.{e}") for s, e in (("color", "jpg"), ("depth", "png"), ("poses", "txt"))]
+    c, d, e = pipeline.load_frame(*ok, intr, synth.T_FIX)
+    assert c.shape == (48, 64, 3) and d.dtype == np.uint16
+    assert np.allclose(e, np.linalg.inv(np.loadtxt(ok[2]) @ synth.T_FIX))
+    wrong = o3d.camera.PinholeCameraIntrinsic(640, 480, 1, 1, 1, 1)
+    with pytest.raises(RuntimeError, match="Unsupported image format"):
+        pipeline.load_frame(*ok, wrong, synth.T_FIX)
+    with pytest.raises(Exception):
+        pipeline.load_frame(ok[0], ok[1], os.path.join(base, "poses", "nope.txt"), intr, synth.T_FIX)
+
+    class FakeVolume:
+        def __init__(self):
+            self.calls = []
+
+        def integrate_sequence(self, d, c, intr_, e, s, t):
+            self.calls.append(len(e))
+
+    triples = [(ok[0], ok[1], ok[2], 1), (ok[0], os.path.join(base, "depth", "nope.png"), ok[2], 2), (ok[0], ok[1], ok[2], 3)]
+    fv, errs = FakeVolume(), []
+    n = pipeline.integrate_files(fv, triples, intr, synth.T_FIX, skip_errors=True, on_error=lambda l, e: errs.append(l))
+    assert n == 2 and fv.calls == [2] and errs == [2]                  # reconstruct_rgbd_filter.py:108-109: skip the frame
+    with pytest.raises(RuntimeError):                                   # reconstruct_rgbd.py: no try -> abort
+        pipeline.integrate_files(FakeVolume(), triples, intr, synth.T_FIX, skip_errors=False)
+
+
+def test_synth_matches_capture_contract():
+    seq = synth.make_sequence("table", 300, subsample=(0, 150))
+    d, c = seq.numpy()
+    assert d.dtype == np.uint16 and d.shape == (2, 480, 640) and c.shape == (2, 480, 640, 3)
+    assert d.max() <= 5000 and (d == 0).any()                          # > 5 m -> 0 (scanner_node.cpp:277-278)
+    assert np.allclose(seq.pose_ros, np.round(seq.pose_ros, 6))
+    T = seq.pose_ros[0] @ synth.T_FIX                                   # optical pose: z looks at the table
+    fwd = T[:3, 2]
+    to_target = np.array([0, 0, 0.5]) - T[:3, 3]
+    assert np.dot(fwd, to_target / np.linalg.norm(to_target)) > 0.999
+    # the analytic table top (z = 0.75) is visible at the image centre
+    pts = T @ np.array([0, 0, d[0, 240, 320] / 1000.0, 1.0])
+    assert abs(pts[2] - 0.75) < 0.01 or abs(pts[2]) < 0.01
+
+
+def test_bench_reference_arm_runs_on_cpu():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--frames", "12", "--cpu-frames", "4"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    import json
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["unit"] == "frames/s"
