@@ -46,6 +46,10 @@ int otslam_version(void);
 /* number of CUDA kernels this library has launched in this process (bench.py "gpu_launches") */
 int64_t otslam_launch_count(void);
 
+/* device self-test of the integration kernel's shared-reciprocal division and ALU floor against
+ * the IEEE intrinsics (__fdiv_rn, F2I) on n pseudo-random operand triples; *mismatches must be 0. */
+int otslam_selftest_division(uint64_t n, uint64_t seed, uint64_t* mismatches, int device);
+
 /* ---- volume life cycle: o3d.pipelines.integration.ScalableTSDFVolume(voxel_length, sdf_trunc,
  *      color_type) (3d_model/reconstruct_rgbd.py:79-83); volume_unit_resolution = 16,
  *      depth_sampling_stride = 4 as in Open3D. `slab` may be NULL. */

@@ -220,3 +220,13 @@ def test_compat_api_per_frame_matches_batch(table_seq):
     bad = o3d.camera.PinholeCameraIntrinsic(320, 240, *seq.fxfycxcy)
     with pytest.raises(RuntimeError, match="Unsupported image format"):
         vol.integrate(rgbd, bad, seq.extrinsic[0])
+
+
+def test_division_selftest():
+    """The integration kernel's shared-reciprocal division / ALU floor must equal __fdiv_rn / F2I for
+    every operand (2^28 pseudo-random triples incl. raw bit patterns: denormals, inf, NaN)."""
+    from otslam_b200 import _lib
+    bad = C.c_uint64(123)
+    for seed in (0, 0x1234567):
+        _lib.check(_lib.lib.otslam_selftest_division(1 << 28, seed, C.byref(bad), 0))
+        assert bad.value == 0
