@@ -118,11 +118,20 @@ def cpu_sample(a, seq_np, cores_hint=None):
     depth, rgb, extr, fxfycxcy = seq_np
     n = len(depth)
     cores = oracle.num_threads()
-    want = a.cpu_frames or max(8, min(n, 6 * cores))
+    if a.cpu_frames:
+        want = a.cpu_frames
+    else:
+        # size the sample for ~12 s of CPU work from a 4-frame probe (bounded by the sequence length)
+        probe = oracle.Volume(a.voxel, 4 * a.voxel)
+        t0 = time.perf_counter()
+        for k in range(0, n, max(1, n // 4))[:4]:
+            probe.integrate(oracle.depth_convert(depth[k], 1000.0, 3.0), rgb[k], fxfycxcy, extr[k])
+        per = (time.perf_counter() - t0) / 4
+        del probe
+        want = int(max(8, min(n, 12.0 / max(per, 1e-4))))
     step = max(1, n // want)
     idx = list(range(0, n, step))[:want]
     vol = oracle.Volume(a.voxel, 4 * a.voxel)
-    # warm the first frame's allocations outside the timed region? No: allocation is part of the loop.
     t0 = time.perf_counter()
     for k in idx:
         d = oracle.depth_convert(depth[k], 1000.0, 3.0)
