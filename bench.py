@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--hd", action="store_true", help="1280x720 / 2 mm large-room config (SURVEY 8d config 4)")
     ap.add_argument("--cpu-frames", type=int, default=0, help="oracle sample size (0 = auto)")
+    ap.add_argument("--slab-thickness", type=int, default=1, help="multi-GPU: blocks per slab (cyclic over ranks)")
+    ap.add_argument("--slab-halo", type=int, default=0, help="multi-GPU: 1 = replicate +1 halo blocks, 0 = exchange planes")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -196,7 +198,7 @@ def run_ours(a):
     W, H = seq.intr[0], seq.intr[1]
     n = len(seq)
     depth_dev, rgb_dev = seq.depth.contiguous(), seq.rgb.contiguous()
-    slab = None if world == 1 else (0, 8, world, rank)
+    slab = None if world == 1 else (0, a.slab_thickness, world, rank, a.slab_halo)
     vol = TSDFVolume(a.voxel, 4 * a.voxel, device=local, slab=slab)
     vol.set_batch(a.batch)
     stream = torch.cuda.Stream()
@@ -259,7 +261,9 @@ def run_ours(a):
                 "algorithmic_bytes_per_launch": bytes_per_launch, "launch_ms": k4_avg_ms,
                 "launches_per_step": k4_launches / max(1, a.steps),
                 "n_upd_per_frame": n_upd / n, "kernel_share_of_step": k4_ms / ms if ms > 0 else None,
-                "other_kernels_ms_per_step": {"pack": prof["pack"][0] / a.steps, "alloc": prof["alloc"][0] / a.steps}}
+                "other_kernels_ms_per_step": {"pack": prof["pack"][0] / a.steps, "alloc": prof["alloc"][0] / a.steps,
+                                              "note": "pack/alloc of batch b+1 run on a second stream UNDER integrate(b); "
+                                                      "their event spans include that contention and are not additive"}}
 
     # ---- end to end through the C ABI with host buffers (rank-local copy of the sequence)
     e2e = None
@@ -297,6 +301,11 @@ def run_ours(a):
         from otslam_b200 import slab as slabmod
         torch.cuda.synchronize()
         t0 = time.perf_counter()
+        halo_planes = 0 if a.slab_halo else slabmod.exchange_halo(vol, rank, world, device=f"cuda:{local}")
+        torch.cuda.synchronize()
+        extra["halo_exchange_ms"] = 1e3 * (time.perf_counter() - t0)
+        extra["halo_planes_received_rank0"] = int(halo_planes)
+        t0 = time.perf_counter()
         pts = slabmod.extract_and_gather_points(vol, rank, world, device=f"cuda:{local}")
         torch.cuda.synchronize()
         extra["extract_gather_ms"] = 1e3 * (time.perf_counter() - t0)
@@ -312,7 +321,10 @@ def run_ours(a):
                 "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": workload_name(a), "frames_per_step": n, "frames_per_launch": a.batch,
-                           "parallelism": "single GPU" if world == 1 else f"x-axis slabs of 8 blocks, cyclic over {world} ranks, +1 block halo",
+                           "parallelism": "single GPU" if world == 1 else (
+                               f"x-axis slabs of {a.slab_thickness} block(s), cyclic over {world} ranks, " +
+                               ("+1 block halo integrated redundantly" if a.slab_halo else
+                                "owned blocks only; boundary planes exchanged once before extraction")),
                            "l2": "inputs (%.0f MB) + volume (%.0f MB) exceed the 126 MB L2; no flush needed" % (
                                n * W * H * 5 / 1e6, stats["n_blocks"] * 65536 / 1e6),
                            "n_blocks": stats["n_blocks"]},

@@ -35,10 +35,13 @@ extern "C" {
 typedef struct otslam_volume otslam_volume;
 
 /* Spatial slab sharding of the block grid across the GPUs of one box: block key k on
- * `axis` is owned by rank (floor(k / thickness) mod n_ranks); a rank also keeps the +1 neighbour
- * blocks of the blocks it owns (halo) so that extraction is local. n_ranks == 1: keep everything. */
+ * `axis` is owned by rank (floor(k / thickness) mod n_ranks).  Extraction needs the +1 neighbour
+ * voxels of owned blocks: halo = 1 integrates the +1 neighbour blocks redundantly on this rank (no
+ * exchange at all); halo = 0 integrates owned blocks only and the ranks exchange the 256-voxel
+ * boundary planes once before extraction (otslam_volume_halo_export / _import).
+ * n_ranks == 1: keep everything. */
 typedef struct {
-    int32_t axis, thickness, n_ranks, rank;
+    int32_t axis, thickness, n_ranks, rank, halo;
 } otslam_slab_spec;
 
 const char* otslam_last_error(void);
@@ -93,6 +96,14 @@ int otslam_volume_num_blocks(otslam_volume* v, int64_t* n_blocks);
 int otslam_volume_export_blocks(otslam_volume* v, int32_t* keys, float* tsdf, float* weight, float* color);
 /* sum of all voxel weights (== number of voxel updates since reset) and voxels with weight > 0 */
 int otslam_volume_stats(otslam_volume* v, int64_t* n_blocks, uint64_t* weight_sum, uint64_t* n_observed);
+
+/* ---- halo exchange for slab.halo == 0 (the path's only inter-GPU exchange besides the final
+ *      gather): export the low-side boundary plane (coordinate 0 on the slab axis; 256 voxel
+ *      records of 16 bytes, opaque) of every owned block whose -axis neighbour block belongs to
+ *      another rank, with that rank as destination; import inserts received planes as non-owned
+ *      blocks.  Call export with NULL buffers to get the count. */
+int otslam_volume_halo_export(otslam_volume* v, int64_t* n, int32_t* keys, int32_t* dest_rank, void* planes);
+int otslam_volume_halo_import(otslam_volume* v, int64_t n, const int32_t* keys, const void* planes);
 
 /* ---- surface extraction: volume.extract_triangle_mesh() (reconstruct_rgbd.py:112) followed by
  *      mesh.compute_vertex_normals() (reconstruct_rgbd.py:113).  extract runs the kernels and

@@ -17,7 +17,8 @@ COLOR_NONE, COLOR_RGB8 = 0, 1
 
 
 class SlabSpec(C.Structure):
-    _fields_ = [("axis", C.c_int32), ("thickness", C.c_int32), ("n_ranks", C.c_int32), ("rank", C.c_int32)]
+    _fields_ = [("axis", C.c_int32), ("thickness", C.c_int32), ("n_ranks", C.c_int32), ("rank", C.c_int32),
+                ("halo", C.c_int32)]
 
 
 if not os.path.exists(SO_PATH):
@@ -45,6 +46,8 @@ _SIGS = {
     "otslam_volume_num_blocks": (_i, [_vp, C.POINTER(_i64)]),
     "otslam_volume_export_blocks": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "otslam_volume_stats": (_i, [_vp, C.POINTER(_i64), C.POINTER(_u64), C.POINTER(_u64)]),
+    "otslam_volume_halo_export": (_i, [_vp, C.POINTER(_i64), _vp, _vp, _vp]),
+    "otslam_volume_halo_import": (_i, [_vp, _i64, _vp, _vp]),
     "otslam_volume_extract_mesh": (_i, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
     "otslam_volume_mesh_copy": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "otslam_volume_extract_points": (_i, [_vp, C.POINTER(_i64)]),

@@ -113,7 +113,7 @@ __device__ inline uint4* block_ptr(uint4* const* chunks, int slot) {
 }
 
 struct SlabSpec {
-    int axis, thickness, n_ranks, rank;
+    int axis, thickness, n_ranks, rank, halo;
 };
 __host__ __device__ inline int floordiv_i(int a, int b) {
     int q = a / b, r = a % b;
@@ -131,7 +131,7 @@ __host__ __device__ inline bool slab_owns(const SlabSpec& s, int kx, int ky, int
 __host__ __device__ inline bool slab_keeps(const SlabSpec& s, int kx, int ky, int kz) {
     if (s.n_ranks <= 1) return true;
     int a = s.axis == 0 ? kx : (s.axis == 1 ? ky : kz);
-    return slab_owner(s, a) == s.rank || slab_owner(s, a - 1) == s.rank;
+    return slab_owner(s, a) == s.rank || (s.halo && slab_owner(s, a - 1) == s.rank);
 }
 
 // simple RAII device buffer for the stateless operators

@@ -17,7 +17,8 @@ struct FrameDev {
 };
 static_assert(sizeof(FrameDev) == 160, "FrameDev layout");
 
-enum CounterIdx { kPoolCount = 0, kListCount = 1, kFlags = 2, kNumCounters = 4 };
+// device counters: [0] pool slots handed out; per batch buffer b: [2+b] work-list length, [4+b] flags
+enum CounterIdx { kPoolCount = 0, kListCount = 2, kFlags = 4, kNumCounters = 8 };
 enum Flags { kFlagHashFull = 1, kFlagKeyRange = 2, kFlagBoxTooLarge = 4 };
 
 struct MeshResult {
@@ -43,8 +44,8 @@ struct otslam_volume {
     int device = 0;
     double voxel_length = 0, sdf_trunc = 0, unit_length = 0;
     int color_type = OTSLAM_COLOR_RGB8;
-    otslam::SlabSpec slab{0, 8, 1, 0};
-    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    otslam::SlabSpec slab{0, 8, 1, 0, 1};
+    cudaStream_t stream = nullptr, copy_stream = nullptr, pre_stream = nullptr;
     bool own_stream = true;
     int batch = otslam::kMaxBatch;
     int64_t frames_integrated = 0;
@@ -53,8 +54,9 @@ struct otslam_volume {
     uint32_t cap = 0;
     uint64_t* d_keys = nullptr;
     int32_t* d_vals = nullptr;     // entry -> pool slot
-    uint32_t* d_masks = nullptr;   // entry -> bit f set when frame f of the current batch touches it
-    int32_t* d_list = nullptr;     // entries touched by the current batch (each once)
+    // double buffered per batch: allocation of batch b+1 runs on pre_stream while batch b integrates
+    uint32_t* d_masks[2] = {nullptr, nullptr};   // entry -> bit f set when frame f of the batch touches it
+    int32_t* d_list[2] = {nullptr, nullptr};     // entries touched by the batch (each once)
 
     // block pool: chunks of kChunkBlocks blocks, 64 KiB per block
     std::vector<uint4*> chunks;
@@ -62,7 +64,9 @@ struct otslam_volume {
     int64_t n_blocks = 0;          // host mirror of the pool counter
 
     int* d_counters = nullptr;
-    int* h_counters = nullptr;     // pinned
+    int* h_counters = nullptr;     // pinned [2][kNumCounters]
+    std::vector<uint4*> h_chunk_table;   // never reallocates (reserved to kMaxChunks): async copies read from it
+    cudaEvent_t ev_pre_done[2] = {nullptr, nullptr}, ev_k4_done[2] = {nullptr, nullptr}, ev_main = nullptr;
 
     // frame staging (double buffered)
     uint16_t* d_raw_depth[2] = {nullptr, nullptr};

@@ -1,9 +1,13 @@
 """Slab-sharded volumes across the GPUs of one box.
 
-Every rank receives every frame and integrates only the blocks of its own x-slabs (plus a
-one-block halo on the +x side), so there is NO collective during integration.  The only exchange
-is the final gather of the extracted geometry to rank 0, done with torch.distributed point-to-point
-ops (ncclSend/ncclRecv over NVLink with the nccl backend; gloo in the CPU tests).
+Every rank receives every frame and integrates only the blocks of its own x-slabs, so there is NO
+collective during integration.  Extraction needs the +1 neighbour voxels of owned blocks; two modes:
+  halo=1  the +1 neighbour blocks are integrated redundantly on this rank (no exchange, (T+1)/T work);
+  halo=0  owned blocks only (perfectly partitioned work, thin slabs balance well) and ONE exchange
+          of the 256-voxel boundary planes before extraction (`exchange_halo`).
+The other exchange is the final gather of the extracted geometry to rank 0.  Both use
+torch.distributed point-to-point ops (ncclSend/ncclRecv over NVLink with the nccl backend; gloo in
+the CPU tests).
 
 Vertices on a slab boundary can be produced by two ranks (the edge is owned by a halo block of one
 of them); both compute them from bit-identical replicated voxels, and rank 0 unifies them by their
@@ -16,9 +20,51 @@ import torch.distributed as dist
 DEFAULT_THICKNESS = 8
 
 
-def slab_spec(rank, world, axis=0, thickness=DEFAULT_THICKNESS):
-    """(axis, thickness, n_ranks, rank) for TSDFVolume(slab=...); None on a single GPU."""
-    return None if world <= 1 else (axis, thickness, world, rank)
+def slab_spec(rank, world, axis=0, thickness=DEFAULT_THICKNESS, halo=1):
+    """(axis, thickness, n_ranks, rank[, halo]) for TSDFVolume(slab=...); None on a single GPU."""
+    if world <= 1:
+        return None
+    return (axis, thickness, world, rank) if halo else (axis, thickness, world, rank, 0)
+
+
+def exchange_halo(vol, rank, world, device="cpu"):
+    """halo=0 mode: send each owned boundary plane to the rank that owns the -axis neighbour block and
+    insert the received planes as non-owned blocks.  Must run after integration and before
+    extraction.  Returns the number of planes received."""
+    if world <= 1:
+        return 0
+    keys, dest, planes = vol.halo_export()
+    rec = planes.shape[1] if planes.ndim == 2 else 0
+    counts = torch.tensor([int((dest == r).sum()) for r in range(world)] + [rec], dtype=torch.int64, device=device)
+    allc = [torch.zeros(world + 1, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(allc, counts)
+    allc = [[int(x) for x in c.tolist()] for c in allc]          # allc[src][dst]
+    rec = max(c[world] for c in allc)
+    ops, send_keep, recv = [], [], []
+    for r in range(world):
+        if r == rank:
+            continue
+        n_out = allc[rank][r]
+        if n_out:
+            sel = dest == r
+            tk = torch.from_numpy(np.ascontiguousarray(keys[sel])).to(device)
+            tp = torch.from_numpy(np.ascontiguousarray(planes[sel])).to(device)
+            send_keep += [tk, tp]
+            ops += [dist.P2POp(dist.isend, tk, r), dist.P2POp(dist.isend, tp, r)]
+        n_in = allc[r][rank]
+        if n_in:
+            rk = torch.empty((n_in, 3), dtype=torch.int32, device=device)
+            rp = torch.empty((n_in, rec), dtype=torch.uint8, device=device)
+            recv.append((rk, rp))
+            ops += [dist.P2POp(dist.irecv, rk, r), dist.P2POp(dist.irecv, rp, r)]
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    got = 0
+    for rk, rp in recv:
+        vol.halo_import(rk.cpu().numpy(), rp.cpu().numpy())
+        got += len(rk)
+    return got
 
 
 def _gatherv(arrays, rank, world, device):

@@ -16,7 +16,9 @@ class TSDFVolume:
         self._h = C.c_void_p()
         spec = None
         if slab is not None:
-            spec = C.byref(_lib.SlabSpec(*[int(x) for x in slab]))
+            axis, thickness, n_ranks, rank = (int(x) for x in slab[:4])
+            halo = int(slab[4]) if len(slab) > 4 else 1
+            spec = C.byref(_lib.SlabSpec(axis, thickness, n_ranks, rank, halo))
         _lib.check(_lib.lib.otslam_volume_create(self.voxel_length, self.sdf_trunc,
                                                  _lib.COLOR_RGB8 if color else _lib.COLOR_NONE, self.device, spec,
                                                  C.byref(self._h)))
@@ -107,6 +109,22 @@ class TSDFVolume:
         nb, ws, no = C.c_int64(0), C.c_uint64(0), C.c_uint64(0)
         _lib.check(_lib.lib.otslam_volume_stats(self._h, C.byref(nb), C.byref(ws), C.byref(no)))
         return {"n_blocks": nb.value, "weight_sum": ws.value, "n_observed": no.value}
+
+    def halo_export(self):
+        """(keys [n,3] i32, dest rank [n] i32, planes [n,4096] u8) for the slab halo exchange."""
+        n = C.c_int64(0)
+        _lib.check(_lib.lib.otslam_volume_halo_export(self._h, C.byref(n), None, None, None))
+        keys = np.empty((n.value, 3), np.int32)
+        dest = np.empty(n.value, np.int32)
+        planes = np.empty((n.value, 4096), np.uint8)
+        if n.value:
+            _lib.check(_lib.lib.otslam_volume_halo_export(self._h, C.byref(n), _lib.ptr(keys), _lib.ptr(dest), _lib.ptr(planes)))
+        return keys, dest, planes
+
+    def halo_import(self, keys, planes):
+        keys = np.ascontiguousarray(keys, np.int32)
+        planes = np.ascontiguousarray(planes, np.uint8)
+        _lib.check(_lib.lib.otslam_volume_halo_import(self._h, len(keys), _lib.ptr(keys), _lib.ptr(planes)))
 
     def extract_triangle_mesh(self, normals=True):
         nv, nf = C.c_int64(0), C.c_int64(0)

@@ -72,7 +72,7 @@ struct Volume {
     double voxel_length, sdf_trunc, unit_length;
     int stride = 4;
     // slab sharding; n_ranks==1 -> keep everything
-    int slab_axis = 0, slab_thickness = 8, slab_ranks = 1, slab_rank = 0;
+    int slab_axis = 0, slab_thickness = 8, slab_ranks = 1, slab_rank = 0, slab_halo = 1;
     std::unordered_map<Key, Block*, KeyHash> blocks;
     ~Volume() { for (auto& kv : blocks) delete kv.second; }
 };
@@ -88,7 +88,8 @@ inline int key_axis(const Key& k, int axis) { return axis == 0 ? k.x : (axis == 
 inline bool slab_keeps(const Volume* v, const Key& k) {
     if (v->slab_ranks <= 1) return true;
     int a = key_axis(k, v->slab_axis);
-    return slab_owner(v, a) == v->slab_rank || slab_owner(v, a - 1) == v->slab_rank;
+    // slab_halo == 0: integrate owned blocks only; the boundary planes are exchanged before extraction
+    return slab_owner(v, a) == v->slab_rank || (v->slab_halo && slab_owner(v, a - 1) == v->slab_rank);
 }
 inline bool slab_owns(const Volume* v, const Key& k) {
     if (v->slab_ranks <= 1) return true;
@@ -279,10 +280,57 @@ void* oracle_volume_create(double voxel_length, double sdf_trunc) {
     v->unit_length = voxel_length * RES;
     return v;
 }
-int oracle_volume_set_slab(void* h, int axis, int thickness, int n_ranks, int rank) {
+int oracle_volume_set_slab(void* h, int axis, int thickness, int n_ranks, int rank, int halo) {
     Volume* v = (Volume*)h;
     if (axis < 0 || axis > 2 || thickness < 1 || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail("bad slab spec");
-    v->slab_axis = axis; v->slab_thickness = thickness; v->slab_ranks = n_ranks; v->slab_rank = rank;
+    v->slab_axis = axis; v->slab_thickness = thickness; v->slab_ranks = n_ranks; v->slab_rank = rank; v->slab_halo = halo ? 1 : 0;
+    return 0;
+}
+
+// Halo exchange for slab_halo == 0: the low-side boundary plane (coordinate 0 on the slab
+// axis, 256 voxels) of every owned block whose -axis neighbour belongs to another rank.  Plane
+// voxel (u, v) = the two other axes in increasing order; per voxel tsdf, weight, colour[3].
+int64_t oracle_volume_halo_export(void* h, int32_t* keys, int32_t* dest, float* tsdf, float* weight, double* color) {
+    Volume* v = (Volume*)h;
+    int64_t n = 0;
+    if (v->slab_ranks <= 1) return 0;
+    for (Block* b : sorted_blocks(v)) {
+        if (!slab_owns(v, b->key)) continue;
+        const int d = slab_owner(v, key_axis(b->key, v->slab_axis) - 1);
+        if (d == v->slab_rank) continue;
+        if (keys) {
+            keys[3 * n] = b->key.x; keys[3 * n + 1] = b->key.y; keys[3 * n + 2] = b->key.z;
+            dest[n] = d;
+            for (int u = 0; u < RES; ++u)
+                for (int w = 0; w < RES; ++w) {
+                    int c[3];
+                    c[v->slab_axis] = 0; c[(v->slab_axis == 0) ? 1 : 0] = u; c[(v->slab_axis == 2) ? 1 : 2] = w;
+                    const int idx = c[0] * 256 + c[1] * 16 + c[2], o = (int)(n * 256 + u * 16 + w);
+                    tsdf[o] = b->tsdf[idx]; weight[o] = b->weight[idx];
+                    for (int k = 0; k < 3; ++k) color[3 * o + k] = b->color[3 * idx + k];
+                }
+        }
+        ++n;
+    }
+    return n;
+}
+int oracle_volume_halo_import(void* h, int64_t n, const int32_t* keys, const float* tsdf, const float* weight, const double* color) {
+    Volume* v = (Volume*)h;
+    for (int64_t i = 0; i < n; ++i) {
+        Key k{keys[3 * i], keys[3 * i + 1], keys[3 * i + 2]};
+        auto it = v->blocks.find(k);
+        if (it == v->blocks.end()) it = v->blocks.emplace(k, new Block(k)).first;
+        Block* b = it->second;
+        for (int u = 0; u < RES; ++u)
+            for (int w = 0; w < RES; ++w) {
+                int c[3];
+                c[v->slab_axis] = 0; c[(v->slab_axis == 0) ? 1 : 0] = u; c[(v->slab_axis == 2) ? 1 : 2] = w;
+                const int idx = c[0] * 256 + c[1] * 16 + c[2];
+                const int64_t o = i * 256 + u * 16 + w;
+                b->tsdf[idx] = tsdf[o]; b->weight[idx] = weight[o];
+                for (int kk = 0; kk < 3; ++kk) b->color[3 * idx + kk] = color[3 * o + kk];
+            }
+    }
     return 0;
 }
 void oracle_volume_destroy(void* h) { delete (Volume*)h; }

@@ -34,7 +34,7 @@ def lib():
         L.oracle_volume_create.restype = C.c_void_p
         L.oracle_volume_create.argtypes = [C.c_double, C.c_double]
         L.oracle_volume_extract_mesh.restype = C.c_void_p
-        for name in ("oracle_volume_num_blocks", "oracle_volume_extract_points", "oracle_zfilter",
+        for name in ("oracle_volume_halo_export", "oracle_volume_num_blocks", "oracle_volume_extract_points", "oracle_zfilter",
                      "oracle_backproject_rgbd", "oracle_voxel_down_sample", "oracle_remove_statistical_outlier",
                      "oracle_grid_to_points"):
             getattr(L, name).restype = C.c_int64
@@ -78,8 +78,9 @@ class Volume:
             raise _err()
         self.voxel_length, self.sdf_trunc = voxel_length, sdf_trunc
         if slab is not None:
-            axis, thickness, n_ranks, rank = slab
-            if lib().oracle_volume_set_slab(self.h, axis, thickness, n_ranks, rank) != 0:
+            axis, thickness, n_ranks, rank = slab[:4]
+            halo = slab[4] if len(slab) > 4 else 1
+            if lib().oracle_volume_set_slab(self.h, axis, thickness, n_ranks, rank, halo) != 0:
                 raise _err()
 
     def __del__(self):
@@ -115,6 +116,28 @@ class Volume:
         col = np.empty((n, 4096, 3), np.float64) if color else None
         lib().oracle_volume_export_blocks(self.h, _p(keys), _p(tsdf), _p(weight), _p(col))
         return keys, tsdf, weight, col
+
+    def halo_export(self):
+        """(keys [n,3] i32, dest rank [n] i32, planes): boundary planes for the halo exchange."""
+        n = int(lib().oracle_volume_halo_export(self.h, None, None, None, None, None))
+        keys = np.empty((n, 3), np.int32); dest = np.empty(n, np.int32)
+        tsdf = np.empty((n, 256), np.float32); w = np.empty((n, 256), np.float32); col = np.empty((n, 256, 3), np.float64)
+        lib().oracle_volume_halo_export(self.h, _p(keys), _p(dest), _p(tsdf), _p(w), _p(col))
+        # one opaque byte record per block so the exchange code is layout agnostic
+        planes = np.concatenate([tsdf.view(np.uint8).reshape(n, -1), w.view(np.uint8).reshape(n, -1),
+                                 col.view(np.uint8).reshape(n, -1)], axis=1) if n else np.zeros((0, 256 * 32), np.uint8)
+        return keys, dest, np.ascontiguousarray(planes)
+
+    def halo_import(self, keys, planes):
+        n = len(keys)
+        if n == 0:
+            return
+        planes = np.ascontiguousarray(planes, np.uint8).reshape(n, 256 * 32)
+        tsdf = np.ascontiguousarray(planes[:, :1024]).view(np.float32)
+        w = np.ascontiguousarray(planes[:, 1024:2048]).view(np.float32)
+        col = np.ascontiguousarray(planes[:, 2048:]).view(np.float64)
+        k = np.ascontiguousarray(keys, np.int32)
+        lib().oracle_volume_halo_import(self.h, C.c_int64(n), _p(k), _p(tsdf), _p(w), _p(col))
 
     def extract_triangle_mesh(self):
         nv, nf = C.c_int64(0), C.c_int64(0)

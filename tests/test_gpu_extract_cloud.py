@@ -64,6 +64,40 @@ def test_slab_union_equals_full_volume(table_seq):
         v.close()
 
 
+@pytest.mark.parametrize("n_ranks,thickness", [(2, 1), (3, 2)])
+def test_halo_exchange_mode_equals_full_volume(table_seq, n_ranks, thickness):
+    """slab.halo = 0: owned blocks only during integration, boundary planes exchanged before extraction
+    (ranks emulated as separate volumes on one GPU; the torch.distributed transport is covered by
+    tests/test_slab_gloo.py)."""
+    from otslam_b200 import slab as slabmod
+    seq, d, c = table_seq
+    full, _ = build_pair(seq, d, c, 0.01)
+    parts = [build_pair(seq, d, c, 0.01, slab=(0, thickness, n_ranks, r, 0))[0] for r in range(n_ranks)]
+    n_owned = [v.num_blocks() for v in parts]
+    assert sum(n_owned) == full.num_blocks()                        # a true partition: no replicated integration
+    assert sum(v.stats()["weight_sum"] for v in parts) == full.stats()["weight_sum"]
+    exports = [v.halo_export() for v in parts]
+    for r, v in enumerate(parts):
+        for src, (keys, dest, planes) in enumerate(exports):
+            sel = dest == r
+            assert src != r or not sel.any()
+            if sel.any():
+                v.halo_import(keys[sel], planes[sel])
+    assert all(v.num_blocks() > n for v, n in zip(parts, n_owned))
+    fv = full.extract_triangle_mesh(normals=False)
+    merged = slabmod.merge_mesh_parts([(p[0], p[1], p[3], p[4]) for p in (v.extract_triangle_mesh(normals=False) for v in parts)])
+    A, B = canon_mesh(fv[0], fv[1], fv[3], fv[4]), canon_mesh(*merged)
+    assert len(A[0]) == len(B[0]) and (A[3] == B[3]).all() and (A[0] == B[0]).all() and (A[2] == B[2]).all()
+    assert np.abs(A[1] - B[1]).max() == 0.0
+    fp, fc, fe = full.extract_point_cloud()
+    pp = [v.extract_point_cloud() for v in parts]
+    pe = np.concatenate([p[2] for p in pp])
+    a, b = lexorder(fe), lexorder(pe)
+    assert len(fe) == len(pe) and (fe[a] == pe[b]).all() and (fp[a] == np.concatenate([p[0] for p in pp])[b]).all()
+    for v in parts + [full]:
+        v.close()
+
+
 def test_empty_volume_extraction():
     from otslam_b200.volume import TSDFVolume
     v = TSDFVolume(0.01, 0.04)

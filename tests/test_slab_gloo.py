@@ -20,11 +20,17 @@ class OracleSlabVolume:
     def extract_point_cloud(self):
         return self.v.extract_point_cloud()
 
+    def halo_export(self):
+        return self.v.halo_export()
+
+    def halo_import(self, keys, planes):
+        return self.v.halo_import(keys, planes)
+
     def extract_triangle_mesh(self):
         return self.v.extract_triangle_mesh()
 
 
-def _worker(rank, world, port, out_path):
+def _worker(rank, world, port, out_path, halo=1, thickness=2):
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
     from oracle import oracle
@@ -34,9 +40,13 @@ def _worker(rank, world, port, out_path):
     intr = (160, 120, 565.6009 / 4, 565.6009 / 4, 80.5, 60.5)
     seq = synth.make_sequence("chair_table", 40, intr=intr, subsample=(0, 10))
     d, c = seq.numpy()
-    vol = oracle.Volume(0.02, 0.08, slab=slab.slab_spec(rank, world, axis=0, thickness=2))
+    vol = oracle.Volume(0.02, 0.08, slab=slab.slab_spec(rank, world, axis=0, thickness=thickness, halo=halo))
     for k in range(len(seq)):                                   # every rank receives every frame
         vol.integrate(oracle.depth_convert(d[k]), c[k], seq.fxfycxcy, seq.extrinsic[k])
+    if not halo:
+        n_owned = vol.num_blocks()
+        got = slab.exchange_halo(OracleSlabVolume(vol), rank, world)
+        assert got > 0 and vol.num_blocks() == n_owned + got
     pts = slab.extract_and_gather_points(OracleSlabVolume(vol), rank, world)
     mesh = slab.extract_and_gather_mesh(OracleSlabVolume(vol), rank, world)
     if rank == 0:
@@ -47,12 +57,17 @@ def _worker(rank, world, port, out_path):
     dist.destroy_process_group()
 
 
-def test_world_size_2_gather_reassembles_full_result(tmp_path):
+import pytest
+
+
+@pytest.mark.parametrize("world,halo,thickness", [(2, 1, 2), (2, 0, 1), (3, 0, 2)])
+def test_world_size_n_gather_reassembles_full_result(tmp_path, world, halo, thickness):
+    """halo=1: replicated +1 blocks, no exchange; halo=0: owned blocks only + boundary-plane exchange."""
     from oracle import oracle
     from otslam_b200 import synth
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     out = str(tmp_path / "rank0.npz")
-    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(world, port, out, halo, thickness), nprocs=world, join=True)
     z = np.load(out)
     intr = (160, 120, 565.6009 / 4, 565.6009 / 4, 80.5, 60.5)
     seq = synth.make_sequence("chair_table", 40, intr=intr, subsample=(0, 10))
