@@ -65,6 +65,10 @@ int otslam_volume_set_stream(otslam_volume* v, void* cuda_stream);
 /* frames fused per block residency in integrate_batch (1..32, default 32) */
 int otslam_volume_set_batch(otslam_volume* v, int frames_per_batch);
 
+/* CTAs per block along z in the integration kernel: 0 = default (1), 1, 2 or 4; results are
+ * bit-identical for every setting */
+int otslam_volume_set_zsplit(otslam_volume* v, int zsplit);
+
 /* kernel timing with CUDA events on the volume's stream (bench.py roofline): enable > 0 switches
  * recording on and zeroes the accumulators, 0 switches it off, < 0 only reads; out_ms /
  * out_launches (nullable, 4 entries: 0 = depth pack, 1 = block allocation, 2 = integration,

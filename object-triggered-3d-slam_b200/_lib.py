@@ -39,6 +39,7 @@ _SIGS = {
     "otslam_volume_reset": (_i, [_vp]),
     "otslam_volume_set_stream": (_i, [_vp, _vp]),
     "otslam_volume_set_batch": (_i, [_vp, _i]),
+    "otslam_volume_set_zsplit": (_i, [_vp, _i]),
     "otslam_volume_profile": (_i, [_vp, _i, _vp, _vp]),
     "otslam_volume_integrate_u16": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _d, _d]),
     "otslam_volume_integrate_f32": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),

@@ -8,9 +8,9 @@
 // reduced sequentially.  The k-NN search is one warp per query over a hashed uniform grid: lanes
 // look up the cells of a ring in parallel, the warp scans their points cooperatively and keeps the
 // k best squared distances (exact FP64, the reference's (dx^2+dy^2)+dz^2 order) in shared memory.
-// The radix sort itself is cub::DeviceRadixSort (CUDA toolkit header library) -- plain plumbing.
-#include <cub/device/device_radix_sort.cuh>
-
+// The stable LSD radix sort (8-bit digits, only as many passes as the keys have significant bits)
+// is hand-written below as well: per-tile histogram -> scan -> stable scatter with warp-level
+// __match_any_sync ranking.
 #include <algorithm>
 #include <cmath>
 #include <vector>
@@ -69,9 +69,31 @@ static int cloud_minmax(const double* d_pts, int64_t n, double* mn, double* mx) 
     return OTSLAM_OK;
 }
 
-// key = floor((p - origin) / cell) per axis, 21 bits each (the host checks the range)
+// key = floor((p - origin) / cell) per axis packed as kx << sh_x | ky << sh_y | kz with just enough
+// bits per axis (the host sizes them from the bounding box), so the sort needs few passes and
+// key order == lexicographic (x, y, z)
+struct KeyLayout {
+    int sh_x, sh_y, bits;
+    uint64_t mask_y, mask_z;
+};
+static int nbits_for(double n_cells) {
+    int b = 1;
+    while (b < 62 && (double)(1ull << b) < n_cells) ++b;
+    return b;
+}
+static KeyLayout make_layout(double nx, double ny, double nz) {
+    const int bx = nbits_for(nx), by = nbits_for(ny), bz = nbits_for(nz);
+    KeyLayout L;
+    L.sh_y = bz; L.sh_x = by + bz; L.bits = bx + by + bz;
+    L.mask_y = (1ull << by) - 1; L.mask_z = (1ull << bz) - 1;
+    return L;
+}
+__host__ __device__ inline uint64_t layout_key(const KeyLayout& L, int x, int y, int z) {
+    return ((uint64_t)(uint32_t)x << L.sh_x) | ((uint64_t)(uint32_t)y << L.sh_y) | (uint64_t)(uint32_t)z;
+}
+
 __global__ void __launch_bounds__(256) cell_key_kernel(const double* __restrict__ pts, int64_t n, double ox, double oy, double oz,
-                                                       double cell, int clamp_hi_x, int clamp_hi_y, int clamp_hi_z,
+                                                       double cell, int clamp_hi_x, int clamp_hi_y, int clamp_hi_z, KeyLayout L,
                                                        uint64_t* __restrict__ keys, int32_t* __restrict__ idx) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -81,17 +103,95 @@ __global__ void __launch_bounds__(256) cell_key_kernel(const double* __restrict_
     if (clamp_hi_x >= 0) {   // k-NN grid: clamp into the grid (voxel_down_sample passes -1: exact keys)
         kx = min(max(kx, 0), clamp_hi_x); ky = min(max(ky, 0), clamp_hi_y); kz = min(max(kz, 0), clamp_hi_z);
     }
-    keys[i] = ((uint64_t)(uint32_t)kx << 42) | ((uint64_t)(uint32_t)ky << 21) | (uint64_t)(uint32_t)kz;
+    keys[i] = layout_key(L, kx, ky, kz);
     idx[i] = (int32_t)i;
 }
 
-static int sort_pairs(DevBuf<uint64_t>& k_in, DevBuf<int32_t>& v_in, DevBuf<uint64_t>& k_out, DevBuf<int32_t>& v_out, int64_t n) {
-    size_t tmp_bytes = 0;
-    OT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in.p, k_out.p, v_in.p, v_out.p, (int)n, 0, 63));
-    DevBuf<uint8_t> tmp;
-    OT_CUDA(tmp.alloc(tmp_bytes));
-    OT_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, k_in.p, k_out.p, v_in.p, v_out.p, (int)n, 0, 63));
-    g_launches.fetch_add(1);
+// ---------------------------------------------------------------------------------------------
+// stable LSD radix sort of (u64 key, i32 value) pairs
+// ---------------------------------------------------------------------------------------------
+constexpr int kSortItems = 8;                         // keys per thread
+constexpr int kSortTile = 256 * kSortItems;           // keys per CTA
+
+__global__ void __launch_bounds__(256) radix_hist_kernel(const uint64_t* __restrict__ keys, int64_t n, int shift, int n_cta,
+                                                         int* __restrict__ hist /*[256][n_cta]*/) {
+    __shared__ int h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * kSortTile;
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+        const int64_t i = base + r * 256 + threadIdx.x;
+        if (i < n) atomicAdd(&h[(int)((keys[i] >> shift) & 0xFF)], 1);
+    }
+    __syncthreads();
+    hist[threadIdx.x * n_cta + blockIdx.x] = h[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(256) radix_scatter_kernel(const uint64_t* __restrict__ keys, const int32_t* __restrict__ vals,
+                                                            int64_t n, int shift, int n_cta, const int64_t* __restrict__ offs,
+                                                            uint64_t* __restrict__ out_keys, int32_t* __restrict__ out_vals) {
+    __shared__ int warp_cnt[8][256];                  // this round: keys per (warp, digit)
+    __shared__ int64_t digit_base[256];               // global offset of this tile's next key of each digit
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    digit_base[t] = offs[(int64_t)t * n_cta + blockIdx.x];
+    const int64_t base = (int64_t)blockIdx.x * kSortTile;
+    for (int r = 0; r < kSortItems; ++r) {
+#pragma unroll
+        for (int w = 0; w < 8; ++w) warp_cnt[w][t] = 0;
+        __syncthreads();
+        const int64_t i = base + r * 256 + t;
+        const bool valid = i < n;
+        uint64_t key = 0;
+        int val = 0, digit = 256 + lane;              // invalid lanes never match anybody
+        if (valid) { key = keys[i]; val = vals[i]; digit = (int)((key >> shift) & 0xFF); }
+        // lanes of the warp holding the same digit, in lane (= index) order: stable rank inside the warp
+        const unsigned peers = __match_any_sync(0xffffffffu, digit);
+        const int rank_in_warp = __popc(peers & ((1u << lane) - 1u));
+        if (valid && rank_in_warp == 0) warp_cnt[wid][digit] = __popc(peers);
+        __syncthreads();
+        int64_t pos = 0;
+        if (valid) {
+            int before = 0;
+            for (int w = 0; w < wid; ++w) before += warp_cnt[w][digit];
+            pos = digit_base[digit] + before + rank_in_warp;
+        }
+        __syncthreads();
+        {   // advance the per-digit bases by this round's totals (thread t owns digit t)
+            int tot = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) tot += warp_cnt[w][t];
+            digit_base[t] += tot;
+        }
+        if (valid) { out_keys[pos] = key; out_vals[pos] = val; }
+        __syncthreads();
+    }
+}
+
+// sorts by the low `bits` bits of the keys; result ends up in (k_out, v_out)
+static int sort_pairs(DevBuf<uint64_t>& k_in, DevBuf<int32_t>& v_in, DevBuf<uint64_t>& k_out, DevBuf<int32_t>& v_out, int64_t n,
+                      int bits = 63) {
+    const int n_cta = (int)((n + kSortTile - 1) / kSortTile);
+    const int passes = std::max(1, (bits + 7) / 8);
+    DevBuf<int> hist;
+    DevBuf<int64_t> offs;
+    OT_CUDA(hist.alloc((size_t)256 * n_cta));
+    OT_CUDA(offs.alloc((size_t)256 * n_cta + 1));
+    uint64_t *ka = k_in.p, *kb = k_out.p;
+    int32_t *va = v_in.p, *vb = v_out.p;
+    for (int p = 0; p < passes; ++p) {
+        radix_hist_kernel<<<n_cta, 256>>>(ka, n, 8 * p, n_cta, hist.p);
+        OT_LAUNCHED();
+        OT_TRY(device_exclusive_scan(hist.p, offs.p, 256 * n_cta, 0));   // digit-major: all tiles of digit 0, then digit 1, ...
+        radix_scatter_kernel<<<n_cta, 256>>>(ka, va, n, 8 * p, n_cta, offs.p, kb, vb);
+        OT_LAUNCHED();
+        std::swap(ka, kb);
+        std::swap(va, vb);
+    }
+    if (ka != k_out.p) {   // odd number of passes leaves the result in the input buffers
+        OT_CUDA(cudaMemcpy(k_out.p, ka, (size_t)n * 8, cudaMemcpyDeviceToDevice));
+        OT_CUDA(cudaMemcpy(v_out.p, va, (size_t)n * 4, cudaMemcpyDeviceToDevice));
+    }
     return OTSLAM_OK;
 }
 
@@ -149,7 +249,7 @@ static int find_segments(const uint64_t* d_keys, int64_t n, DevBuf<int32_t>& seg
 // one thread per voxel: sequential FP64 sums in point-index order (stable sort => ascending indices)
 __global__ void __launch_bounds__(128) voxel_mean_kernel(const double* __restrict__ pts, const double* __restrict__ cols,
                                                          const uint64_t* __restrict__ keys, const int32_t* __restrict__ idx,
-                                                         const int32_t* __restrict__ seg_start, int64_t n_seg,
+                                                         const int32_t* __restrict__ seg_start, int64_t n_seg, KeyLayout L,
                                                          double* __restrict__ out_pts, double* __restrict__ out_cols,
                                                          int32_t* __restrict__ out_keys, int32_t* __restrict__ out_counts) {
     const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -172,9 +272,9 @@ __global__ void __launch_bounds__(128) voxel_mean_kernel(const double* __restric
     }
     const uint64_t k = keys[b];
     if (out_keys) {
-        out_keys[3 * m] = (int32_t)((k >> 42) & 0x1FFFFF);
-        out_keys[3 * m + 1] = (int32_t)((k >> 21) & 0x1FFFFF);
-        out_keys[3 * m + 2] = (int32_t)(k & 0x1FFFFF);
+        out_keys[3 * m] = (int32_t)(k >> L.sh_x);
+        out_keys[3 * m + 1] = (int32_t)((k >> L.sh_y) & L.mask_y);
+        out_keys[3 * m + 2] = (int32_t)(k & L.mask_z);
     }
     if (out_counts) out_counts[m] = e - b;
 }
@@ -205,6 +305,7 @@ struct KnnArgs {
     int k;
     double mn[3], cell;
     int dim[3];
+    KeyLayout L;
     double* dbar;               // [n] original order
 };
 
@@ -288,7 +389,7 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_mean_dist_kernel(KnnArgs a
                 }
                 const int x = c[0] + dx, y = c[1] + dy, z = c[2] + dz;
                 if (x >= 0 && x < a.dim[0] && y >= 0 && y < a.dim[1] && z >= 0 && z < a.dim[2]) {
-                    const uint64_t key = ((uint64_t)(uint32_t)x << 42) | ((uint64_t)(uint32_t)y << 21) | (uint64_t)(uint32_t)z;
+                    const uint64_t key = layout_key(a.L, x, y, z);
                     uint32_t h = hash_key(key) & a.cap_mask;
                     for (;;) {
                         const uint64_t hk = a.hkeys[h];
@@ -431,15 +532,16 @@ int otslam_cloud_voxel_down_sample(const double* points, const double* colors, i
         vmin[a] = mn[a] - voxel_size * 0.5;
         const double vmax = mx[a] + voxel_size * 0.5;
         if (voxel_size * 2147483647.0 < vmax - vmin[a]) return set_error(OTSLAM_ERR_INVALID, "[VoxelDownSample] voxel_size is too small.");
-        if (std::floor((mx[a] - vmin[a]) / voxel_size) >= 2097152.0)
-            return set_error(OTSLAM_ERR_OVERFLOW, "[VoxelDownSample] more than 2^21 voxels along one axis is not supported on the GPU path");
     }
+    const KeyLayout L = make_layout(std::floor((mx[0] - vmin[0]) / voxel_size) + 1.0, std::floor((mx[1] - vmin[1]) / voxel_size) + 1.0,
+                                    std::floor((mx[2] - vmin[2]) / voxel_size) + 1.0);
+    if (L.bits > 63) return set_error(OTSLAM_ERR_OVERFLOW, "[VoxelDownSample] voxel grid needs more than 63 key bits on the GPU path");
     DevBuf<uint64_t> k0, k1;
     DevBuf<int32_t> i0, i1;
     OT_CUDA(k0.alloc(n)); OT_CUDA(k1.alloc(n)); OT_CUDA(i0.alloc(n)); OT_CUDA(i1.alloc(n));
-    cell_key_kernel<<<(unsigned)((n + 255) / 256), 256>>>(dp.p, n, vmin[0], vmin[1], vmin[2], voxel_size, -1, -1, -1, k0.p, i0.p);
+    cell_key_kernel<<<(unsigned)((n + 255) / 256), 256>>>(dp.p, n, vmin[0], vmin[1], vmin[2], voxel_size, -1, -1, -1, L, k0.p, i0.p);
     OT_LAUNCHED();
-    OT_TRY(sort_pairs(k0, i0, k1, i1, n));
+    OT_TRY(sort_pairs(k0, i0, k1, i1, n, L.bits));
     DevBuf<int32_t> seg;
     int64_t m = 0;
     OT_TRY(find_segments(k1.p, n, seg, &m));
@@ -448,7 +550,7 @@ int otslam_cloud_voxel_down_sample(const double* points, const double* colors, i
     DevBuf<double> op, oc;
     DevBuf<int32_t> ok, on;
     OT_CUDA(op.alloc(m * 3)); OT_CUDA(oc.alloc(m * 3)); OT_CUDA(ok.alloc(m * 3)); OT_CUDA(on.alloc(m));
-    voxel_mean_kernel<<<(unsigned)((m + 127) / 128), 128>>>(dp.p, colors ? dc.p : nullptr, k1.p, i1.p, seg.p, m, op.p, oc.p, ok.p, on.p);
+    voxel_mean_kernel<<<(unsigned)((m + 127) / 128), 128>>>(dp.p, colors ? dc.p : nullptr, k1.p, i1.p, seg.p, m, L, op.p, oc.p, ok.p, on.p);
     OT_LAUNCHED();
     OT_CUDA(cudaMemcpy(out_points, op.p, m * 24, cudaMemcpyDeviceToHost));
     if (colors && out_colors) OT_CUDA(cudaMemcpy(out_colors, oc.p, m * 24, cudaMemcpyDeviceToHost));
@@ -487,10 +589,11 @@ int otslam_cloud_remove_statistical_outlier(const double* points, int64_t n, int
     DevBuf<uint64_t> k0, k1;
     DevBuf<int32_t> i0, i1;
     OT_CUDA(k0.alloc(n)); OT_CUDA(k1.alloc(n)); OT_CUDA(i0.alloc(n)); OT_CUDA(i1.alloc(n));
+    a.L = make_layout(a.dim[0], a.dim[1], a.dim[2]);
     cell_key_kernel<<<(unsigned)((n + 255) / 256), 256>>>(dp.p, n, a.mn[0], a.mn[1], a.mn[2], cell, a.dim[0] - 1, a.dim[1] - 1,
-                                                         a.dim[2] - 1, k0.p, i0.p);
+                                                         a.dim[2] - 1, a.L, k0.p, i0.p);
     OT_LAUNCHED();
-    OT_TRY(sort_pairs(k0, i0, k1, i1, n));
+    OT_TRY(sort_pairs(k0, i0, k1, i1, n, a.L.bits));
     DevBuf<int32_t> seg;
     int64_t n_seg = 0;
     OT_TRY(find_segments(k1.p, n, seg, &n_seg));

@@ -48,6 +48,7 @@ struct otslam_volume {
     cudaStream_t stream = nullptr, copy_stream = nullptr, pre_stream = nullptr;
     bool own_stream = true;
     int batch = otslam::kMaxBatch;
+    int zsplit = 0;                // CTAs per block along z in the integration kernel: 0 = auto, 1, 2, 4
     int64_t frames_integrated = 0;
 
     // block hash: open addressing, entry index is the handle used by the per-batch work list

@@ -39,6 +39,9 @@ class TSDFVolume:
     def set_batch(self, n):
         _lib.check(_lib.lib.otslam_volume_set_batch(self._h, int(n)))
 
+    def set_zsplit(self, zs):
+        _lib.check(_lib.lib.otslam_volume_set_zsplit(self._h, int(zs)))
+
     def profile(self, enable=None):
         """Per-kernel CUDA-event totals {pack, alloc, integrate}: (ms, launches) accumulated so far.
         enable=True (re)starts recording from zero, False stops it, None only reads."""

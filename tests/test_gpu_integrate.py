@@ -38,7 +38,7 @@ def assert_parity(gv, ov, color=True):
 
 
 @pytest.mark.parametrize("vl", [0.01, 0.005])
-@pytest.mark.parametrize("mode", ["per_frame", "batch_host", "batch_device", "batch_of_1", "batch_of_5"])
+@pytest.mark.parametrize("mode", ["per_frame", "batch_host", "batch_device", "batch_of_1", "batch_of_5", "zsplit_1", "zsplit_2", "zsplit_4"])
 def test_integration_parity(table_seq, vl, mode):
     from otslam_b200.volume import TSDFVolume
     seq, d, c = table_seq
@@ -54,6 +54,8 @@ def test_integration_parity(table_seq, vl, mode):
             gv.set_batch(1)
         if mode == "batch_of_5":
             gv.set_batch(5)
+        if mode.startswith("zsplit"):
+            gv.set_zsplit(int(mode[-1]))          # CTAs per block along z: must not change a single bit
         gv.integrate_batch(d, c, seq.fxfycxcy, seq.extrinsic)
     gt, ot = assert_parity(gv, ov)
     assert (gt == ot).all(), "the f32 running mean is expected to be reproduced bit for bit"
