@@ -147,6 +147,11 @@ int otslam_cloud_voxel_down_sample(const double* points, const double* colors, i
 /* PointCloud.remove_statistical_outlier(nb_neighbors, std_ratio) (north_star); out_indices sized n */
 int otslam_cloud_remove_statistical_outlier(const double* points, int64_t n, int nb_neighbors, double std_ratio,
                                             int64_t* out_indices, int64_t* n_out, double* mean_dist, int device);
+/* PointCloud.compute_point_cloud_distance(target): distance from every source point to its nearest
+ * target point -- the accuracy / completeness metric of the reference's evaluation scripts
+ * (eval/eval_table_chair/eval_table_chair.py:106-119; SURVEY 8f "next" row 3) */
+int otslam_cloud_nn_distance(const double* source, int64_t n_source, const double* target, int64_t n_target,
+                             double* out_dist, int device);
 /* create_map_cloud's pixel loop (fusion/hybrid_map.py:45-55); out sized w*h*3 (or NULL to count) */
 int otslam_grid_to_points(const uint8_t* gray, int width, int height, double resolution, double origin_x,
                           double origin_y, int threshold, double* out_points, int64_t* n_out, int device);

@@ -295,7 +295,11 @@ __global__ void __launch_bounds__(256) cell_hash_build_kernel(const uint64_t* __
 }
 
 struct KnnArgs {
-    const double* pts;          // original order
+    const double* pts;          // target cloud, original order
+    const double* qpts;         // query points (== pts for the outlier filter)
+    const int32_t* qidx;        // query visit order -> query index (null: identity)
+    int64_t nq;
+    int mode;                   // 0: dbar = mean of the k sqrt distances (A.8); 1: nearest-neighbour distance
     const int32_t* idx;         // sorted position -> original index
     const int32_t* seg_start;   // [n_seg+1]
     const uint64_t* hkeys;
@@ -332,11 +336,11 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_mean_dist_kernel(KnnArgs a
     __shared__ double s_sorted[kKnnWarps][kKnnMaxK];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t qpos = (int64_t)blockIdx.x * kKnnWarps + wid;
-    if (qpos >= a.n) return;
+    if (qpos >= a.nq) return;
     double* best = s_best[wid];
     double* sorted = s_sorted[wid];
-    const int qi = a.idx[qpos];
-    const double q[3] = {a.pts[3 * (size_t)qi], a.pts[3 * (size_t)qi + 1], a.pts[3 * (size_t)qi + 2]};
+    const int64_t qi = a.qidx ? (int64_t)a.qidx[qpos] : qpos;
+    const double q[3] = {a.qpts[3 * (size_t)qi], a.qpts[3 * (size_t)qi + 1], a.qpts[3 * (size_t)qi + 2]};
     int c[3];
 #pragma unroll
     for (int ax = 0; ax < 3; ++ax) {
@@ -451,7 +455,8 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_mean_dist_kernel(KnnArgs a
     if (lane == 0) {
         double s = 0.0;
         for (int j = 0; j < found; ++j) s = __dadd_rn(s, __dsqrt_rn(sorted[j]));
-        a.dbar[qi] = found > 0 ? __ddiv_rn(s, (double)found) : -1.0;
+        if (a.mode == 1) a.dbar[qi] = found > 0 ? __dsqrt_rn(sorted[0]) : -1.0;
+        else a.dbar[qi] = found > 0 ? __ddiv_rn(s, (double)found) : -1.0;
     }
 }
 
@@ -607,7 +612,7 @@ int otslam_cloud_remove_statistical_outlier(const double* points, int64_t n, int
     OT_LAUNCHED();
     DevBuf<double> dbar, scal;
     OT_CUDA(dbar.alloc(n)); OT_CUDA(scal.alloc(1));
-    a.pts = dp.p; a.idx = i1.p; a.seg_start = seg.p; a.hkeys = hk.p; a.hvals = hv.p; a.cap_mask = cap - 1; a.n = n; a.k = k; a.dbar = dbar.p;
+    a.pts = dp.p; a.qpts = dp.p; a.qidx = i1.p; a.nq = n; a.mode = 0; a.idx = i1.p; a.seg_start = seg.p; a.hkeys = hk.p; a.hvals = hv.p; a.cap_mask = cap - 1; a.n = n; a.k = k; a.dbar = dbar.p;
     knn_mean_dist_kernel<<<(unsigned)((n + kKnnWarps - 1) / kKnnWarps), kKnnWarps * 32>>>(a);
     OT_LAUNCHED();
     if (mean_dist) OT_CUDA(cudaMemcpy(mean_dist, dbar.p, n * 8, cudaMemcpyDeviceToHost));
@@ -638,6 +643,55 @@ int otslam_cloud_remove_statistical_outlier(const double* points, int64_t n, int
     sor_select_kernel<<<n_cta, 256>>>(dbar.p, n, thr, base.p, nullptr, oidx.p);
     OT_LAUNCHED();
     OT_CUDA(cudaMemcpy(out_indices, oidx.p, m * 8, cudaMemcpyDeviceToHost));
+    return OTSLAM_OK;
+}
+
+int otslam_cloud_nn_distance(const double* source, int64_t n_source, const double* target, int64_t n_target, double* out_dist,
+                             int device) {
+    if (n_source < 0 || n_target < 0 || (n_source && (!source || !out_dist)) || (n_target && !target))
+        return set_error(OTSLAM_ERR_INVALID, "bad arguments");
+    if (n_source == 0) return OTSLAM_OK;
+    if (n_target == 0) return set_error(OTSLAM_ERR_INVALID, "[ComputePointCloudDistance] target cloud is empty");
+    if (n_target > 0x7fffffffLL || n_source > 0x7fffffffLL) return set_error(OTSLAM_ERR_OVERFLOW, "more than 2^31 points");
+    OT_TRY(use_device(device));
+    DevBuf<double> dt, dsrc, dout;
+    OT_CUDA(dt.alloc(n_target * 3)); OT_CUDA(dsrc.alloc(n_source * 3)); OT_CUDA(dout.alloc(n_source));
+    OT_CUDA(cudaMemcpy(dt.p, target, n_target * 24, cudaMemcpyHostToDevice));
+    OT_CUDA(cudaMemcpy(dsrc.p, source, n_source * 24, cudaMemcpyHostToDevice));
+    KnnArgs a;
+    double mx[3];
+    OT_TRY(cloud_minmax(dt.p, n_target, a.mn, mx));
+    const double ext[3] = {mx[0] - a.mn[0], mx[1] - a.mn[1], mx[2] - a.mn[2]};
+    const double vol = std::max(ext[0], 1e-9) * std::max(ext[1], 1e-9) * std::max(ext[2], 1e-9);
+    double cell = std::cbrt(vol / std::max(1.0, (double)n_target / 2.0));
+    cell = std::max(cell, std::max(ext[0], std::max(ext[1], ext[2])) / 1024.0);
+    if (!(cell > 0.0) || !std::isfinite(cell)) cell = 1.0;
+    a.cell = cell;
+    for (int ax = 0; ax < 3; ++ax) a.dim[ax] = std::max(1, (int)std::floor(ext[ax] / cell) + 1);
+    a.L = make_layout(a.dim[0], a.dim[1], a.dim[2]);
+    DevBuf<uint64_t> k0, k1;
+    DevBuf<int32_t> i0, i1;
+    OT_CUDA(k0.alloc(n_target)); OT_CUDA(k1.alloc(n_target)); OT_CUDA(i0.alloc(n_target)); OT_CUDA(i1.alloc(n_target));
+    cell_key_kernel<<<(unsigned)((n_target + 255) / 256), 256>>>(dt.p, n_target, a.mn[0], a.mn[1], a.mn[2], cell, a.dim[0] - 1,
+                                                                a.dim[1] - 1, a.dim[2] - 1, a.L, k0.p, i0.p);
+    OT_LAUNCHED();
+    OT_TRY(sort_pairs(k0, i0, k1, i1, n_target, a.L.bits));
+    DevBuf<int32_t> seg;
+    int64_t n_seg = 0;
+    OT_TRY(find_segments(k1.p, n_target, seg, &n_seg));
+    uint32_t cap = 1024;
+    while ((int64_t)cap < 2 * n_seg) cap <<= 1;
+    DevBuf<uint64_t> hk;
+    DevBuf<int32_t> hv;
+    OT_CUDA(hk.alloc(cap)); OT_CUDA(hv.alloc(cap));
+    OT_CUDA(cudaMemset(hk.p, 0xFF, (size_t)cap * 8));
+    cell_hash_build_kernel<<<(unsigned)((n_seg + 255) / 256), 256>>>(k1.p, seg.p, n_seg, hk.p, hv.p, cap - 1);
+    OT_LAUNCHED();
+    a.pts = dt.p; a.qpts = dsrc.p; a.qidx = nullptr; a.nq = n_source; a.mode = 1; a.idx = i1.p; a.seg_start = seg.p;
+    a.hkeys = hk.p; a.hvals = hv.p; a.cap_mask = cap - 1; a.n = n_target; a.k = 1; a.dbar = dout.p;
+    knn_mean_dist_kernel<<<(unsigned)((n_source + kKnnWarps - 1) / kKnnWarps), kKnnWarps * 32>>>(a);
+    OT_LAUNCHED();
+    OT_CUDA(cudaMemcpy(out_dist, dout.p, n_source * 8, cudaMemcpyDeviceToHost));
     return OTSLAM_OK;
 }
 

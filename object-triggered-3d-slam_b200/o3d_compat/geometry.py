@@ -207,6 +207,15 @@ class PointCloud:
             pc._colors = np.ascontiguousarray(cols[:n.value])
         return pc
 
+    def compute_point_cloud_distance(self, target):
+        """Distance from each point of this cloud to its nearest neighbour in `target` (the accuracy /
+        completeness metric of /root/reference/eval/eval_table_chair/eval_table_chair.py:106-119)."""
+        n = len(self._points)
+        out = np.empty(n, np.float64)
+        _lib.check(_lib.lib.otslam_cloud_nn_distance(_lib.ptr(self._points), n, _lib.ptr(target._points), len(target._points),
+                                                     _lib.ptr(out), 0))
+        return out
+
     def voxel_down_sample(self, voxel_size):
         """check_one_frame.py:28; output ordered by voxel key."""
         n = len(self._points)

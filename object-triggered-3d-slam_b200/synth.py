@@ -244,17 +244,10 @@ def make_sequence(scene="table", n_frames=8, intr=REF_INTRINSICS, device="cpu", 
 def write_capture_tree(seq, base_dir, label="Object_0", start=1):
     """Write color/<label>_<n>.jpg, depth/<label>_<n>.png, poses/<label>_<n>.txt
     (scanner_node.cpp:268-299)."""
-    import cv2
-    for sub in ("color", "depth", "poses"):
-        os.makedirs(os.path.join(base_dir, sub), exist_ok=True)
+    from . import capture
     depth, rgb = seq.numpy()
     for k in range(len(seq)):
-        n = start + k
-        cv2.imwrite(os.path.join(base_dir, "color", f"{label}_{n}.jpg"), rgb[k][..., ::-1])
-        cv2.imwrite(os.path.join(base_dir, "depth", f"{label}_{n}.png"), depth[k])
-        with open(os.path.join(base_dir, "poses", f"{label}_{n}.txt"), "w") as f:
-            for r in range(4):
-                f.write(" ".join("%.6f" % v for v in seq.pose_ros[k][r]) + "\n")
+        capture.save_frame(base_dir, label, start + k, rgb[k], depth[k], seq.pose_ros[k])
 
 
 def occupancy_map(w=2000, h=2000, occupied_frac=0.02, seed=0):

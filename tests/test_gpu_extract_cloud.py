@@ -185,6 +185,23 @@ def test_zfilter_vds_sor(mesh):
     assert idx == oracle.remove_statistical_outlier(noisy[:5], 20, 2.0)[0].tolist()
 
 
+def test_point_cloud_distance_vs_ckdtree(mesh):
+    """eval metric (accuracy / completeness = mean nearest-neighbour distance both ways)."""
+    import otslam_b200.o3d_compat as o3d
+    v, col, f, n = mesh
+    a, _, _, _ = oracle.sample_uniform(v, None, None, f, 30000, seed=2)
+    b, _, _, _ = oracle.sample_uniform(v, None, None, f, 50000, seed=3)
+    b = b + np.array([0.3, -0.2, 0.05])                       # partially overlapping: queries outside the target grid too
+    pa, pb = o3d.geometry.PointCloud(a), o3d.geometry.PointCloud(b)
+    d_ab = pa.compute_point_cloud_distance(pb)
+    d_ba = pb.compute_point_cloud_distance(pa)
+    assert np.allclose(d_ab, cKDTree(b).query(a)[0], rtol=1e-12, atol=1e-15)
+    assert np.allclose(d_ba, cKDTree(a).query(b)[0], rtol=1e-12, atol=1e-15)
+    assert (pa.compute_point_cloud_distance(pa) == 0).all()
+    with pytest.raises(RuntimeError):
+        pa.compute_point_cloud_distance(o3d.geometry.PointCloud())
+
+
 def test_grid_points_and_merge_pack(tmp_path):
     import otslam_b200.o3d_compat as o3d
     from otslam_b200 import _lib, synth

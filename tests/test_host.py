@@ -172,3 +172,15 @@ def test_bench_reference_arm_runs_on_cpu():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["unit"] == "frames/s"
+
+
+def test_capture_depth_conversion_matches_scanner_node():
+    """scanner_node.cpp:277-281: NaN -> 0, > 5 m -> 0, x1000, round-half-even, saturate."""
+    from otslam_b200 import capture
+    d = np.array([[np.nan, 0.0, 0.0004, 0.0005, 0.0015, 1.2345, 4.9999, 5.0, 5.0001, 70.0]], np.float32)
+    out = capture.depth_to_u16_mm(d)
+    assert out.dtype == np.uint16
+    exp = [0 if (np.isnan(x) or x > np.float32(5.0)) else int(np.rint(np.float64(x) * 1000.0)) for x in d[0]]
+    assert out[0].tolist() == exp
+    assert out[0, 0] == 0 and out[0, 6] == 5000 and out[0, 7] == 5000 and out[0, 8] == 0 and out[0, 9] == 0 and out[0, 4] == 2
+    assert capture.pose_text(np.eye(4)).splitlines()[3] == "0.000000 0.000000 0.000000 1.000000"
