@@ -176,32 +176,70 @@ __global__ void __launch_bounds__(256) tri_area_kernel(const double* __restrict_
     area[t] = __dmul_rn(0.5, __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(x0, x0), __dmul_rn(x1, x1)), __dmul_rn(x2, x2))));
 }
 
-// Sequential-order FP64 sum / prefix over n values with ONE warp: coalesced 32-wide loads, then the
-// 32 values are added in index order (every lane keeps the same running value).  Bit-identical to
-// a scalar loop; this is the only way to reproduce the reference's sequential accumulations.
-//   mode 0: out[0] = sum(in)                       (surface_area += area)
-//   mode 1: in-place inclusive prefix of in[i]/div  (cdf[t] = area[t]/total + cdf[t-1])
+// Sequential-order FP64 sum / prefix over n values (the reference's scalar accumulations:
+// `surface_area += area`, `cdf[t] = area[t]/total + cdf[t-1]`, the mean / sigma sums of the outlier
+// filter).  FP addition is not associative, so the adds MUST happen in index order: one warp streams
+// the array through shared memory in 1024-element stages (coalesced loads of the next stage are in
+// flight while the current one is consumed, element transforms are applied in parallel), and lane 0
+// walks each stage with the dependent DADD chain -- the only inherently serial part (~10 cycles per
+// element).  Bit-identical to the scalar loop.
+//   mode 0: out[0] = sum(x)                         mode 1: in-place inclusive prefix of x[i] / *div
+//   mode 2: out[0] = sum(x > 0 ? x : 0)             mode 3: out[0] = sum(x > 0 ? (x - mean)^2 : 0)
+constexpr int kOrdStage = 1024;
 __global__ void __launch_bounds__(32) ordered_accumulate_kernel(double* __restrict__ io, int64_t n, int mode, const double* __restrict__ div,
-                                                                double* __restrict__ out) {
+                                                                double mean, double* __restrict__ out) {
+    __shared__ double buf[kOrdStage];
     const int lane = threadIdx.x;
     const double dv = (mode == 1) ? *div : 1.0;
+    double nxt[kOrdStage / 32];
+    auto load_stage = [&](int64_t base) {
+#pragma unroll
+        for (int k = 0; k < kOrdStage / 32; ++k) {
+            const int64_t i = base + k * 32 + lane;
+            nxt[k] = (i < n) ? io[i] : 0.0;
+        }
+    };
     double acc = 0.0;
     bool first = true;
-    for (int64_t b = 0; b < n; b += 32) {
-        const int64_t i = b + lane;
-        double v = (i < n) ? io[i] : 0.0;
-        if (mode == 1) v = __ddiv_rn(v, dv);
-        double mineout = 0.0;
-        const int cnt = (int)min((int64_t)32, n - b);
-        for (int j = 0; j < cnt; ++j) {
-            const double vj = __shfl_sync(0xffffffffu, v, j);
-            acc = first ? vj : __dadd_rn(acc, vj);   // first element: cdf[0] = a[0]/total, sum starts at 0.0 + a[0] == a[0]
-            first = false;
-            if (j == lane) mineout = acc;
+    load_stage(0);
+    for (int64_t base = 0; base < n; base += kOrdStage) {
+#pragma unroll
+        for (int k = 0; k < kOrdStage / 32; ++k) {
+            double v = nxt[k];
+            if (mode == 1) v = __ddiv_rn(v, dv);
+            else if (mode == 2) v = v > 0.0 ? v : 0.0;
+            else if (mode == 3) v = v > 0.0 ? __dmul_rn(__dsub_rn(v, mean), __dsub_rn(v, mean)) : 0.0;
+            buf[k * 32 + lane] = v;
         }
-        if (mode == 1 && i < n) io[i] = mineout;
+        if (base + kOrdStage < n) load_stage(base + kOrdStage);     // in flight during the serial walk
+        __syncwarp();
+        const int cnt = (int)min((int64_t)kOrdStage, n - base);
+        if (lane == 0) {
+            int j = 0;
+            if (first) { acc = buf[0]; if (mode == 1) buf[0] = acc; j = 1; first = false; }
+#pragma unroll 8
+            for (; j < cnt; ++j) {
+                acc = __dadd_rn(acc, buf[j]);
+                if (mode == 1) buf[j] = acc;
+            }
+        }
+        __syncwarp();
+        if (mode == 1) {
+#pragma unroll
+            for (int k = 0; k < kOrdStage / 32; ++k) {
+                const int64_t i = base + k * 32 + lane;
+                if (i < n) io[i] = buf[k * 32 + lane];
+            }
+        }
+        __syncwarp();
     }
-    if (mode == 0 && lane == 0) out[0] = acc;
+    if (mode != 1 && lane == 0) out[0] = (n > 0) ? acc : 0.0;
+}
+
+int device_ordered_sum(double* d_x, int64_t n, int mode, const double* d_div, double mean, double* d_out, cudaStream_t s) {
+    ordered_accumulate_kernel<<<1, 32, 0, s>>>(d_x, n, mode, d_div, mean, d_out);
+    OT_LAUNCHED();
+    return OTSLAM_OK;
 }
 
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
@@ -386,10 +424,8 @@ int otslam_mesh_sample_uniform(const double* vertices, const double* colors, con
     OT_CUDA(op.alloc(n_samples * 3));
     tri_area_kernel<<<(unsigned)((n_faces + 255) / 256), 256>>>(dv.p, df.p, n_faces, area.p);
     OT_LAUNCHED();
-    ordered_accumulate_kernel<<<1, 32>>>(area.p, n_faces, 0, nullptr, total.p);
-    OT_LAUNCHED();
-    ordered_accumulate_kernel<<<1, 32>>>(area.p, n_faces, 1, total.p, nullptr);
-    OT_LAUNCHED();
+    OT_TRY(device_ordered_sum(area.p, n_faces, 0, nullptr, 0.0, total.p, 0));
+    OT_TRY(device_ordered_sum(area.p, n_faces, 1, total.p, 0.0, nullptr, 0));
     sample_kernel<<<(unsigned)((n_samples + 255) / 256), 256>>>(dv.p, has_c ? dc.p : nullptr, has_n ? dn.p : nullptr, df.p, n_faces,
                                                                area.p, n_samples, seed, op.p, oc.p, on.p);
     OT_LAUNCHED();

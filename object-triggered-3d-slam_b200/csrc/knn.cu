@@ -460,24 +460,8 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_mean_dist_kernel(KnnArgs a
     }
 }
 
-// sequential-order sum over n values with one warp (see cloud.cu: ordered_accumulate_kernel):
-//   mode 0: sum of (x > 0 ? x : 0)            mode 1: sum of (x > 0 ? (x-mean)^2 : 0)
-__global__ void __launch_bounds__(32) ordered_stat_kernel(const double* __restrict__ x, int64_t n, int mode, double mean,
-                                                          double* __restrict__ out) {
-    const int lane = threadIdx.x;
-    double acc = 0.0;
-    for (int64_t b = 0; b < n; b += 32) {
-        const int64_t i = b + lane;
-        double v = 0.0;
-        if (i < n) {
-            const double d = x[i];
-            if (d > 0.0) v = (mode == 0) ? d : __dmul_rn(__dsub_rn(d, mean), __dsub_rn(d, mean));
-        }
-        const int cnt = (int)min((int64_t)32, n - b);
-        for (int j = 0; j < cnt; ++j) acc = __dadd_rn(acc, __shfl_sync(0xffffffffu, v, j));
-    }
-    if (lane == 0) out[0] = acc;
-}
+// sequential-order sums for the global mean / sigma: cloud.cu's ordered accumulation, modes 2 and 3
+int device_ordered_sum(double* d_x, int64_t n, int mode, const double* d_div, double mean, double* d_out, cudaStream_t s);
 
 __global__ void __launch_bounds__(256) sor_select_kernel(const double* __restrict__ dbar, int64_t n, double thr,
                                                          const int64_t* __restrict__ base, int* __restrict__ counts,
@@ -618,13 +602,11 @@ int otslam_cloud_remove_statistical_outlier(const double* points, int64_t n, int
     if (mean_dist) OT_CUDA(cudaMemcpy(mean_dist, dbar.p, n * 8, cudaMemcpyDeviceToHost));
     // global statistics in sequential index order; scalars finished on the host in FP64
     double sum = 0.0, sq = 0.0;
-    ordered_stat_kernel<<<1, 32>>>(dbar.p, n, 0, 0.0, scal.p);
-    OT_LAUNCHED();
+    OT_TRY(device_ordered_sum(dbar.p, n, 2, nullptr, 0.0, scal.p, 0));
     OT_CUDA(cudaMemcpy(&sum, scal.p, 8, cudaMemcpyDeviceToHost));
     const int64_t valid = n;   // the query point is its own first neighbour, so every point has >= 1
     const double mean = sum / (double)valid;
-    ordered_stat_kernel<<<1, 32>>>(dbar.p, n, 1, mean, scal.p);
-    OT_LAUNCHED();
+    OT_TRY(device_ordered_sum(dbar.p, n, 3, nullptr, mean, scal.p, 0));
     OT_CUDA(cudaMemcpy(&sq, scal.p, 8, cudaMemcpyDeviceToHost));
     const double sd = valid > 1 ? std::sqrt(sq / (double)(valid - 1)) : 0.0;
     const double thr = mean + std_ratio * sd;
