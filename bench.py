@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--cpu-frames", type=int, default=0, help="oracle sample size (0 = auto)")
     ap.add_argument("--slab-thickness", type=int, default=1, help="multi-GPU: blocks per slab (cyclic over ranks)")
     ap.add_argument("--slab-halo", type=int, default=0, help="multi-GPU: 1 = replicate +1 halo blocks, 0 = exchange planes")
+    ap.add_argument("--emulate-world", type=int, default=0, help="dev: single GPU integrating only rank 0's slabs of an N-rank run")
+    ap.add_argument("--zsplit", type=int, default=0, help="dev: CTAs per block along z in the integration kernel")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -194,8 +196,12 @@ def run_ours(a):
     n = len(seq)
     depth_dev, rgb_dev = seq.depth.contiguous(), seq.rgb.contiguous()
     slab = None if world == 1 else (0, a.slab_thickness, world, rank, a.slab_halo)
+    if world == 1 and a.emulate_world > 1:
+        slab = (0, a.slab_thickness, a.emulate_world, 0, a.slab_halo)
     vol = TSDFVolume(a.voxel, 4 * a.voxel, device=local, slab=slab)
     vol.set_batch(a.batch)
+    if a.zsplit:
+        vol.set_zsplit(a.zsplit)
     stream = torch.cuda.Stream()
     vol.set_stream(stream.cuda_stream)
     torch.cuda.synchronize()

@@ -65,8 +65,8 @@ int otslam_volume_set_stream(otslam_volume* v, void* cuda_stream);
 /* frames fused per block residency in integrate_batch (1..32, default 32) */
 int otslam_volume_set_batch(otslam_volume* v, int frames_per_batch);
 
-/* CTAs per block along z in the integration kernel: 0 = default (1), 1, 2 or 4; results are
- * bit-identical for every setting */
+/* CTAs per block along z in the integration kernel: 0 = automatic (2 when a batch touches fewer
+ * than 800 blocks, else 1), 1, 2 or 4; results are bit-identical for every setting */
 int otslam_volume_set_zsplit(otslam_volume* v, int zsplit);
 
 /* kernel timing with CUDA events on the volume's stream (bench.py roofline): enable > 0 switches
