@@ -28,12 +28,7 @@ _filter.save_dir = save_dir
 Z_FILTER_THRESHOLD = _filter.Z_FILTER_THRESHOLD
 
 
-def reconstruct_range(obj_name, start_frame, end_frame):
-    print("\n========================================")
-    print(f"🛠️  Processing: {obj_name} (Frames {start_frame} -> {end_frame})")
-    print("========================================")
-    volume = o3d.pipelines.integration.ScalableTSDFVolume(
-        voxel_length=VOXEL_LENGTH, sdf_trunc=SDF_TRUNC, color_type=o3d.pipelines.integration.TSDFVolumeColorType.RGB8)
+def _range_triples(start_frame, end_frame):
     triples = []
     for i in range(start_frame, end_frame + 1):
         c_path = os.path.join(color_dir, f"{FILE_PREFIX}_{i}.jpg")
@@ -42,10 +37,15 @@ def reconstruct_range(obj_name, start_frame, end_frame):
             continue
         triples.append((c_path, os.path.join(depth_dir, f"{FILE_PREFIX}_{i}.png"),
                         os.path.join(pose_dir, f"{FILE_PREFIX}_{i}.txt"), i))
-    frames_processed = pipeline.integrate_files(
-        volume, triples, intrinsics, T_fix, DEPTH_SCALE, DEPTH_TRUNC, skip_errors=True,
-        progress=lambda label, i, n: print(f"\r   Integrate: Frame {label}", end="", flush=True),
-        on_error=lambda label, e: print(f"\n   ⚠️ Error on frame {label}: {e}"))
+    return triples
+
+
+def _new_volume():
+    return o3d.pipelines.integration.ScalableTSDFVolume(
+        voxel_length=VOXEL_LENGTH, sdf_trunc=SDF_TRUNC, color_type=o3d.pipelines.integration.TSDFVolumeColorType.RGB8)
+
+
+def _finish(obj_name, volume, frames_processed):
     if frames_processed == 0:
         print(f"\n❌ No frames were integrated for {obj_name}. Check your ranges or file paths.")
         return
@@ -55,10 +55,35 @@ def reconstruct_range(obj_name, start_frame, end_frame):
     _filter.filter_and_save(mesh, obj_name)
 
 
+def reconstruct_range(obj_name, start_frame, end_frame):
+    print("\n========================================")
+    print(f"🛠️  Processing: {obj_name} (Frames {start_frame} -> {end_frame})")
+    print("========================================")
+    volume = _new_volume()
+    frames_processed = pipeline.integrate_files(
+        volume, _range_triples(start_frame, end_frame), intrinsics, T_fix, DEPTH_SCALE, DEPTH_TRUNC, skip_errors=True,
+        progress=lambda label, i, n: print(f"\r   Integrate: Frame {label}", end="", flush=True),
+        on_error=lambda label, e: print(f"\n   ⚠️ Error on frame {label}: {e}"))
+    _finish(obj_name, volume, frames_processed)
+
+
 def main():
     print(f"Starting reconstruction for {len(OBJECT_RANGES)} objects...")
-    for name, (start, end) in OBJECT_RANGES.items():
-        reconstruct_range(name, start, end)
+    if os.environ.get("OTSLAM_PARALLEL_OBJECTS", "0") not in ("", "0"):
+        # config 3: every object is an independent volume -> integrate them concurrently on the GPU
+        jobs, names = [], []
+        for name, (start, end) in OBJECT_RANGES.items():
+            jobs.append((_new_volume(), _range_triples(start, end),
+                         dict(intrinsics=intrinsics, T_fix=T_fix, depth_scale=DEPTH_SCALE, depth_trunc=DEPTH_TRUNC, skip_errors=True,
+                              on_error=lambda label, e: print(f"\n   ⚠️ Error on frame {label}: {e}"))))
+            names.append(name)
+        counts = pipeline.integrate_many(jobs)
+        for name, (vol, _, _), n in zip(names, jobs, counts):
+            print(f"\n🛠️  Processing: {name} ({n} frames integrated)")
+            _finish(name, vol, n)
+    else:
+        for name, (start, end) in OBJECT_RANGES.items():
+            reconstruct_range(name, start, end)
     print("\n🎉 All reconstructions finished!")
 
 

@@ -58,6 +58,20 @@ def integrate_files(volume, triples, intrinsics, T_fix, depth_scale=1000.0, dept
     return done
 
 
+def integrate_many(jobs, max_workers=None):
+    """Config 3 (multi_reconstruct_rgbd_filter.py: several objects, each its own volume): run the
+    independent per-object frame loops CONCURRENTLY on one GPU.  Each volume owns its CUDA streams and
+    the C-ABI calls release the GIL, so the kernels of small per-object volumes (which alone cannot
+    fill 148 SMs) overlap on the device.  jobs = [(volume, triples, kwargs)]; returns the frame counts
+    in job order.  Results are identical to running the jobs one after the other."""
+    from concurrent.futures import ThreadPoolExecutor
+    if not jobs:
+        return []
+    with ThreadPoolExecutor(max_workers=max_workers or len(jobs)) as ex:
+        futs = [ex.submit(integrate_files, vol, triples, **kw) for vol, triples, kw in jobs]
+        return [f.result() for f in futs]
+
+
 def stdout_progress(fmt):
     def cb(label, i, n):
         sys.stdout.write(fmt.format(label=label, i=i, n=n))

@@ -44,6 +44,28 @@ out["integrate_batch_api_pageable_fps"] = len(seq) / (time.perf_counter() - t0)
 st = vol.stats()
 out["volume"] = st
 
+# ---- config 3: 4 objects, each its own volume (reference defaults 1 cm / 4 cm), sequential vs concurrent
+from concurrent.futures import ThreadPoolExecutor
+import torch
+nf3 = 16 if small else 150
+objs3 = []
+for scene in ("table", "chair", "cone", "cardboard"):
+    sq = synth.make_sequence(scene, nf3, device="cuda")
+    hd_ = torch.empty(sq.depth.shape, dtype=sq.depth.dtype, pin_memory=True); hd_.copy_(sq.depth)
+    hc_ = torch.empty(sq.rgb.shape, dtype=sq.rgb.dtype, pin_memory=True); hc_.copy_(sq.rgb)
+    objs3.append((TSDFVolume(0.01, 0.04), hd_, hc_, sq))
+torch.cuda.synchronize()
+def run_obj(o):
+    o[0].reset(); o[0].integrate_batch(o[1], o[2], o[3].fxfycxcy, o[3].extrinsic); return o[0].stats()["weight_sum"]
+for o in objs3: run_obj(o)
+t0 = time.perf_counter(); seq_sums = [run_obj(o) for o in objs3]; t_seq = time.perf_counter() - t0
+with ThreadPoolExecutor(4) as ex:
+    t0 = time.perf_counter(); par_sums = list(ex.map(run_obj, objs3)); t_par = time.perf_counter() - t0
+out["config3_4objects_sequential_fps"] = 4 * nf3 / t_seq
+out["config3_4objects_concurrent_fps"] = 4 * nf3 / t_par
+out["config3_results_equal"] = seq_sums == par_sums
+for o in objs3: o[0].close()
+
 # ---- extraction (K5/K6/K7)
 t, mesh = timed(lambda: vol.extract_triangle_mesh(), 2)
 verts, cols, nrm, faces, ek = mesh
