@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--slab-thickness", type=int, default=1, help="multi-GPU: blocks per slab (cyclic over ranks)")
     ap.add_argument("--slab-halo", type=int, default=0, help="multi-GPU: 1 = replicate +1 halo blocks, 0 = exchange planes")
     ap.add_argument("--emulate-world", type=int, default=0, help="dev: single GPU integrating only rank 0's slabs of an N-rank run")
+    ap.add_argument("--emulate-rank", type=int, default=0, help="dev: which rank's slabs --emulate-world integrates")
+    ap.add_argument("--slab-axis", type=int, default=0, help="multi-GPU: 0/1/2 = x/y/z slabs, 3 = diagonal (x+y+z) slabs")
     ap.add_argument("--zsplit", type=int, default=0, help="dev: CTAs per block along z in the integration kernel")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -195,9 +197,9 @@ def run_ours(a):
     W, H = seq.intr[0], seq.intr[1]
     n = len(seq)
     depth_dev, rgb_dev = seq.depth.contiguous(), seq.rgb.contiguous()
-    slab = None if world == 1 else (0, a.slab_thickness, world, rank, a.slab_halo)
+    slab = None if world == 1 else (a.slab_axis, a.slab_thickness, world, rank, a.slab_halo)
     if world == 1 and a.emulate_world > 1:
-        slab = (0, a.slab_thickness, a.emulate_world, 0, a.slab_halo)
+        slab = (a.slab_axis, a.slab_thickness, a.emulate_world, a.emulate_rank, a.slab_halo)
     vol = TSDFVolume(a.voxel, 4 * a.voxel, device=local, slab=slab)
     vol.set_batch(a.batch)
     if a.zsplit:

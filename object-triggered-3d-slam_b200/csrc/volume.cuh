@@ -17,8 +17,9 @@ struct FrameDev {
 };
 static_assert(sizeof(FrameDev) == 160, "FrameDev layout");
 
-// device counters: [0] pool slots handed out; per batch buffer b: [2+b] work-list length, [4+b] flags
-enum CounterIdx { kPoolCount = 0, kListCount = 2, kFlags = 4, kNumCounters = 8 };
+constexpr int kNB = 3;          // batch buffers: allocation runs up to two batches ahead of integration
+// device counters: [0] pool slots handed out; per batch buffer b: [2+b] work-list length, [5+b] flags
+enum CounterIdx { kPoolCount = 0, kListCount = 2, kFlags = 5, kNumCounters = 8 };
 enum Flags { kFlagHashFull = 1, kFlagKeyRange = 2, kFlagBoxTooLarge = 4 };
 
 struct MeshResult {
@@ -55,9 +56,9 @@ struct otslam_volume {
     uint32_t cap = 0;
     uint64_t* d_keys = nullptr;
     int32_t* d_vals = nullptr;     // entry -> pool slot
-    // double buffered per batch: allocation of batch b+1 runs on pre_stream while batch b integrates
-    uint32_t* d_masks[2] = {nullptr, nullptr};   // entry -> bit f set when frame f of the batch touches it
-    int32_t* d_list[2] = {nullptr, nullptr};     // entries touched by the batch (each once)
+    // kNB-buffered per batch: allocation of batches b+1, b+2 runs on pre_stream while batch b integrates
+    uint32_t* d_masks[otslam::kNB] = {};   // entry -> bit f set when frame f of the batch touches it
+    int32_t* d_list[otslam::kNB] = {};     // entries touched by the batch (each once)
 
     // block pool: chunks of kChunkBlocks blocks, 64 KiB per block
     std::vector<uint4*> chunks;
@@ -65,19 +66,19 @@ struct otslam_volume {
     int64_t n_blocks = 0;          // host mirror of the pool counter
 
     int* d_counters = nullptr;
-    int* h_counters = nullptr;     // pinned [2][kNumCounters]
+    int* h_counters = nullptr;     // pinned [kNB][kNumCounters]
     std::vector<uint4*> h_chunk_table;   // never reallocates (reserved to kMaxChunks): async copies read from it
-    cudaEvent_t ev_pre_done[2] = {nullptr, nullptr}, ev_k4_done[2] = {nullptr, nullptr}, ev_main = nullptr;
+    cudaEvent_t ev_pre_done[otslam::kNB] = {}, ev_k4_done[otslam::kNB] = {}, ev_main = nullptr;
 
-    // frame staging (double buffered)
-    uint16_t* d_raw_depth[2] = {nullptr, nullptr};
-    uint8_t* d_raw_rgb[2] = {nullptr, nullptr};
-    uint2* d_packed[2] = {nullptr, nullptr};
+    // frame staging (kNB buffers)
+    uint16_t* d_raw_depth[otslam::kNB] = {};
+    uint8_t* d_raw_rgb[otslam::kNB] = {};
+    uint2* d_packed[otslam::kNB] = {};
     size_t raw_frames_cap = 0, raw_px_cap = 0, packed_cap = 0;
     size_t raw_depth_bytes_per_px = 2;
-    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_raw_free[2] = {nullptr, nullptr};
-    otslam::FrameDev* d_frames[2] = {nullptr, nullptr};
-    otslam::FrameDev* h_frames = nullptr;  // pinned [2][kMaxBatch]
+    cudaEvent_t ev_copied[otslam::kNB] = {}, ev_raw_free[otslam::kNB] = {};
+    otslam::FrameDev* d_frames[otslam::kNB] = {};
+    otslam::FrameDev* h_frames = nullptr;  // pinned [kNB][kMaxBatch]
 
     // depth->camera-distance multiplier image, cached per intrinsics
     float* d_mult = nullptr;
