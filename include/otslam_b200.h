@@ -48,6 +48,10 @@ const char* otslam_last_error(void);
 int otslam_version(void);
 /* number of CUDA kernels this library has launched in this process (bench.py "gpu_launches") */
 int64_t otslam_launch_count(void);
+/* device-side duration (CUDA events, ms) of the kernel section of the last stateless operator or
+ * extraction call made by this thread, host<->device copies excluded; -1 if none (bench.py's
+ * post-stage rooflines) */
+double otslam_last_op_device_ms(void);
 
 /* device self-test of the integration kernel's shared-reciprocal division and ALU floor against
  * the IEEE intrinsics (__fdiv_rn, F2I) on n pseudo-random operand triples; *mismatches must be 0. */

@@ -33,6 +33,7 @@ _SIGS = {
     "otslam_last_error": (C.c_char_p, []),
     "otslam_version": (_i, []),
     "otslam_launch_count": (_i64, []),
+    "otslam_last_op_device_ms": (_d, []),
     "otslam_selftest_division": (_i, [_u64, _u64, C.POINTER(_u64), _i]),
     "otslam_volume_create": (_i, [_d, _d, _i, _i, C.POINTER(SlabSpec), C.POINTER(_vp)]),
     "otslam_volume_destroy": (_i, [_vp]),
@@ -103,3 +104,7 @@ def ptr(a):
 
 def launch_count():
     return int(lib.otslam_launch_count())
+
+
+def last_op_device_ms():
+    return float(lib.otslam_last_op_device_ms())

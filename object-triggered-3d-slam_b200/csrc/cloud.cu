@@ -422,6 +422,7 @@ int otslam_mesh_sample_uniform(const double* vertices, const double* colors, con
     if (has_c) { OT_CUDA(dc.alloc(n_vertices * 3)); OT_CUDA(cudaMemcpy(dc.p, colors, n_vertices * 24, cudaMemcpyHostToDevice)); OT_CUDA(oc.alloc(n_samples * 3)); }
     if (has_n) { OT_CUDA(dn.alloc(n_vertices * 3)); OT_CUDA(cudaMemcpy(dn.p, normals, n_vertices * 24, cudaMemcpyHostToDevice)); OT_CUDA(on.alloc(n_samples * 3)); }
     OT_CUDA(op.alloc(n_samples * 3));
+    OpTimer timer;
     tri_area_kernel<<<(unsigned)((n_faces + 255) / 256), 256>>>(dv.p, df.p, n_faces, area.p);
     OT_LAUNCHED();
     OT_TRY(device_ordered_sum(area.p, n_faces, 0, nullptr, 0.0, total.p, 0));
@@ -429,6 +430,7 @@ int otslam_mesh_sample_uniform(const double* vertices, const double* colors, con
     sample_kernel<<<(unsigned)((n_samples + 255) / 256), 256>>>(dv.p, has_c ? dc.p : nullptr, has_n ? dn.p : nullptr, df.p, n_faces,
                                                                area.p, n_samples, seed, op.p, oc.p, on.p);
     OT_LAUNCHED();
+    timer.stop();
     OT_CUDA(cudaMemcpy(out_points, op.p, n_samples * 24, cudaMemcpyDeviceToHost));
     if (has_c) OT_CUDA(cudaMemcpy(out_colors, oc.p, n_samples * 24, cudaMemcpyDeviceToHost));
     if (has_n) OT_CUDA(cudaMemcpy(out_normals, on.p, n_samples * 24, cudaMemcpyDeviceToHost));
@@ -449,6 +451,7 @@ int otslam_cloud_zfilter(const double* points, const double* colors, int64_t n, 
     DevBuf<int> counts;
     DevBuf<int64_t> base;
     cudaStream_t s = 0;
+    OpTimer timer;
     auto launch = [&](int n_cta, const int64_t* b, int* cnt) -> int {
         zfilter_kernel<<<n_cta, 256, 0, s>>>(dp.p, has_c ? dc.p : nullptr, n, zmin, b, cnt, op.p, oc.p);
         OT_LAUNCHED();
@@ -461,6 +464,7 @@ int otslam_cloud_zfilter(const double* points, const double* colors, int64_t n, 
     OT_CUDA(op.alloc(m * 3));
     if (has_c) OT_CUDA(oc.alloc(m * 3));
     OT_TRY(launch((int)((n + kItemsPerCta - 1) / kItemsPerCta), base.p, nullptr));
+    timer.stop();
     OT_CUDA(cudaMemcpy(out_points, op.p, m * 24, cudaMemcpyDeviceToHost));
     if (has_c) OT_CUDA(cudaMemcpy(out_colors, oc.p, m * 24, cudaMemcpyDeviceToHost));
     return OTSLAM_OK;
@@ -478,6 +482,7 @@ int otslam_grid_to_points(const uint8_t* gray, int width, int height, double res
     DevBuf<int64_t> base;
     DevBuf<double> op;
     cudaStream_t s = 0;
+    OpTimer timer;
     auto launch = [&](int n_cta, const int64_t* b, int* cnt) -> int {
         grid_points_kernel<<<n_cta, 256, 0, s>>>(di.p, width, height, resolution, origin_x, origin_y, threshold, b, cnt, op.p);
         OT_LAUNCHED();
@@ -489,6 +494,7 @@ int otslam_grid_to_points(const uint8_t* gray, int width, int height, double res
     if (m == 0 || !out_points) return OTSLAM_OK;
     OT_CUDA(op.alloc(m * 3));
     OT_TRY(launch((int)((n + kItemsPerCta - 1) / kItemsPerCta), base.p, nullptr));
+    timer.stop();
     OT_CUDA(cudaMemcpy(out_points, op.p, m * 24, cudaMemcpyDeviceToHost));
     return OTSLAM_OK;
 }
@@ -539,8 +545,10 @@ int otslam_cloud_merge_pack(int n_clouds, const double* const* points, const dou
     }
     MergeArgs a;
     a.pts = dpp.p; a.cols = dcp.p; a.offsets = doff.p; a.paint = paint ? dpaint.p : nullptr; a.n_clouds = n_clouds; a.total = total;
+    OpTimer timer;
     merge_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(a, dout.p);
     OT_LAUNCHED();
+    timer.stop();
     OT_CUDA(cudaMemcpyAsync(out_records, dout.p, total * 27, cudaMemcpyDeviceToHost, s));
     OT_CUDA(cudaStreamSynchronize(s));
     return OTSLAM_OK;

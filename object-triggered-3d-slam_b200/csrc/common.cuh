@@ -13,6 +13,7 @@ namespace otslam {
 
 extern thread_local std::string g_last_error;
 extern std::atomic<int64_t> g_launches;
+extern thread_local double g_last_op_ms;
 
 inline int set_error(int code, const std::string& msg) {
     g_last_error = msg;
@@ -128,6 +129,10 @@ __host__ __device__ inline bool slab_owns(const SlabSpec& s, int kx, int ky, int
     int a = s.axis == 0 ? kx : (s.axis == 1 ? ky : kz);
     return slab_owner(s, a) == s.rank;
 }
+// the same on the slab-axis coordinate alone
+__host__ __device__ inline bool slab_keeps_coord(const SlabSpec& s, int a) {
+    return slab_owner(s, a) == s.rank || (s.halo && slab_owner(s, a - 1) == s.rank);
+}
 __host__ __device__ inline bool slab_keeps(const SlabSpec& s, int kx, int ky, int kz) {
     if (s.n_ranks <= 1) return true;
     int a = s.axis == 0 ? kx : (s.axis == 1 ? ky : kz);
@@ -144,6 +149,30 @@ struct DevBuf {
         if (p) { cudaFree(p); p = nullptr; }
         n = count;
         return cudaMalloc((void**)&p, (count ? count : 1) * sizeof(T));
+    }
+};
+
+// Device-side duration of a stateless operator's kernel section (uploads before it and downloads
+// after it excluded): events on the operators' stream, read back by otslam_last_op_device_ms().
+struct OpTimer {
+    cudaEvent_t a = nullptr, b = nullptr;
+    bool stopped = false;
+    cudaStream_t st;
+    explicit OpTimer(cudaStream_t s = 0) : st(s) {
+        g_last_op_ms = -1.0;
+        if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) { a = b = nullptr; return; }
+        cudaEventRecord(a, st);
+    }
+    void stop() {
+        if (!stopped && b) cudaEventRecord(b, st);
+        stopped = true;
+    }
+    ~OpTimer() {
+        stop();
+        float ms = 0.f;
+        if (b && cudaEventSynchronize(b) == cudaSuccess && cudaEventElapsedTime(&ms, a, b) == cudaSuccess) g_last_op_ms = ms;
+        if (a) cudaEventDestroy(a);
+        if (b) cudaEventDestroy(b);
     }
 };
 

@@ -494,6 +494,7 @@ int otslam_volume_extract_mesh(otslam_volume* v, int64_t* n_vertices, int64_t* n
     OT_TRY(upload_tables());
     v->mesh.release();
     *n_vertices = 0; *n_faces = 0;
+    OpTimer timer(v->stream);
     ExtractCtx c;
     DevBuf<uint64_t> dk;
     DevBuf<int32_t> ds;
@@ -568,6 +569,7 @@ int otslam_volume_extract_points(otslam_volume* v, int64_t* n_points) {
     OT_TRY(use_device(v->device));
     v->points.release();
     *n_points = 0;
+    OpTimer timer(v->stream);
     ExtractCtx c;
     DevBuf<uint64_t> dk;
     DevBuf<int32_t> ds;

@@ -514,6 +514,7 @@ int otslam_cloud_voxel_down_sample(const double* points, const double* colors, i
     OT_CUDA(dp.alloc(n * 3));
     OT_CUDA(cudaMemcpy(dp.p, points, n * 24, cudaMemcpyHostToDevice));
     if (colors) { OT_CUDA(dc.alloc(n * 3)); OT_CUDA(cudaMemcpy(dc.p, colors, n * 24, cudaMemcpyHostToDevice)); }
+    OpTimer timer;
     double mn[3], mx[3];
     OT_TRY(cloud_minmax(dp.p, n, mn, mx));
     double vmin[3];
@@ -541,6 +542,7 @@ int otslam_cloud_voxel_down_sample(const double* points, const double* colors, i
     OT_CUDA(op.alloc(m * 3)); OT_CUDA(oc.alloc(m * 3)); OT_CUDA(ok.alloc(m * 3)); OT_CUDA(on.alloc(m));
     voxel_mean_kernel<<<(unsigned)((m + 127) / 128), 128>>>(dp.p, colors ? dc.p : nullptr, k1.p, i1.p, seg.p, m, L, op.p, oc.p, ok.p, on.p);
     OT_LAUNCHED();
+    timer.stop();
     OT_CUDA(cudaMemcpy(out_points, op.p, m * 24, cudaMemcpyDeviceToHost));
     if (colors && out_colors) OT_CUDA(cudaMemcpy(out_colors, oc.p, m * 24, cudaMemcpyDeviceToHost));
     if (out_keys) OT_CUDA(cudaMemcpy(out_keys, ok.p, m * 12, cudaMemcpyDeviceToHost));
@@ -563,6 +565,7 @@ int otslam_cloud_remove_statistical_outlier(const double* points, int64_t n, int
     DevBuf<double> dp;
     OT_CUDA(dp.alloc(n * 3));
     OT_CUDA(cudaMemcpy(dp.p, points, n * 24, cudaMemcpyHostToDevice));
+    OpTimer timer;
     KnnArgs a;
     double mx[3];
     OT_TRY(cloud_minmax(dp.p, n, a.mn, mx));
@@ -624,6 +627,7 @@ int otslam_cloud_remove_statistical_outlier(const double* points, int64_t n, int
     OT_CUDA(oidx.alloc(m));
     sor_select_kernel<<<n_cta, 256>>>(dbar.p, n, thr, base.p, nullptr, oidx.p);
     OT_LAUNCHED();
+    timer.stop();
     OT_CUDA(cudaMemcpy(out_indices, oidx.p, m * 8, cudaMemcpyDeviceToHost));
     return OTSLAM_OK;
 }
@@ -640,6 +644,7 @@ int otslam_cloud_nn_distance(const double* source, int64_t n_source, const doubl
     OT_CUDA(dt.alloc(n_target * 3)); OT_CUDA(dsrc.alloc(n_source * 3)); OT_CUDA(dout.alloc(n_source));
     OT_CUDA(cudaMemcpy(dt.p, target, n_target * 24, cudaMemcpyHostToDevice));
     OT_CUDA(cudaMemcpy(dsrc.p, source, n_source * 24, cudaMemcpyHostToDevice));
+    OpTimer timer;
     KnnArgs a;
     double mx[3];
     OT_TRY(cloud_minmax(dt.p, n_target, a.mn, mx));
@@ -673,6 +678,7 @@ int otslam_cloud_nn_distance(const double* source, int64_t n_source, const doubl
     a.hkeys = hk.p; a.hvals = hv.p; a.cap_mask = cap - 1; a.n = n_target; a.k = 1; a.dbar = dout.p;
     knn_mean_dist_kernel<<<(unsigned)((n_source + kKnnWarps - 1) / kKnnWarps), kKnnWarps * 32>>>(a);
     OT_LAUNCHED();
+    timer.stop();
     OT_CUDA(cudaMemcpy(out_dist, dout.p, n_source * 8, cudaMemcpyDeviceToHost));
     return OTSLAM_OK;
 }

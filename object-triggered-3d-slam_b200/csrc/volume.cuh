@@ -59,6 +59,7 @@ struct otslam_volume {
     // kNB-buffered per batch: allocation of batches b+1, b+2 runs on pre_stream while batch b integrates
     uint32_t* d_masks[otslam::kNB] = {};   // entry -> bit f set when frame f of the batch touches it
     int32_t* d_list[otslam::kNB] = {};     // entries touched by the batch (each once)
+    int32_t* d_order[otslam::kNB] = {};    // the same entries, most-frames-first (launch order of the integration CTAs)
 
     // block pool: chunks of kChunkBlocks blocks, 64 KiB per block
     std::vector<uint4*> chunks;
