@@ -180,11 +180,16 @@ def post_stage(a, vol, n_blocks, peak):
         out[name] = e
         return r
 
-    verts, cols, nrm, faces, _ = run("extract_mesh+normals", lambda: vol.extract_triangle_mesh(),
-                                     lambda r: 8 * 4096 * n_blocks + 48 * len(r[0]) + 12 * len(r[3]))
-    out["extract_mesh+normals"].update(vertices=int(len(verts)), faces=int(len(faces)))
-    mesh = o3d.geometry.TriangleMesh()
-    mesh.vertices, mesh.vertex_colors, mesh.vertex_normals, mesh.triangles = verts, cols, nrm, faces
+    # reconstruct_rgbd_filter.py:113-123 as the drop-in runs it: the mesh stays in HBM (lazy TriangleMesh)
+    def extract():
+        m = o3d.geometry.TriangleMesh()
+        nv, nf = vol.extract_mesh_resident(owner=m)
+        m._attach_resident(vol, nv, nf, True)
+        m.compute_vertex_normals()
+        return m
+
+    mesh = run("extract_mesh+normals", extract, lambda m: 8 * 4096 * n_blocks + 48 * len(m.vertices) + 12 * len(m.triangles))
+    out["extract_mesh+normals"].update(vertices=int(len(mesh.vertices)), faces=int(len(mesh.triangles)))
 
     def zfilter(pc, zmin=0.03):
         n = len(pc.points)
@@ -205,6 +210,11 @@ def post_stage(a, vol, n_blocks, peak):
         sel = run("remove_statistical_outlier" + tag, lambda: flt.remove_statistical_outlier(20, 2.0),
                   lambda r: 24 * n * 2 + 8 * n + 36 * len(r[1]), nb_neighbors=20, std_ratio=2.0)
         out["remove_statistical_outlier" + tag].update(points_in=n, kept=int(len(sel[1])))
+    # reconstruct_rgbd.py writes the mesh instead: the one-off download of the resident arrays
+    t0 = time.perf_counter()
+    mesh._materialize()
+    out["mesh_download_for_write_triangle_mesh"] = {"wall_ms": 1e3 * (time.perf_counter() - t0),
+                                                    "bytes": int(len(mesh.vertices)) * 72 + int(len(mesh.triangles)) * 12}
     out["total_wall_ms_config1_stage"] = sum(out[k]["wall_ms"] for k in (
         "extract_mesh+normals", "sample_points_uniformly", "z_mask", "voxel_down_sample", "remove_statistical_outlier"))
     return out

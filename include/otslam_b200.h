@@ -52,10 +52,19 @@ int64_t otslam_launch_count(void);
  * extraction call made by this thread, host<->device copies excluded; -1 if none (bench.py's
  * post-stage rooflines) */
 double otslam_last_op_device_ms(void);
+/* operators keep their device temporaries in a per-device cache (cudaMalloc / cudaFree cost more
+ * than their kernels); this returns the cached blocks to the driver */
+int otslam_trim_scratch(void);
 
 /* device self-test of the integration kernel's shared-reciprocal division and ALU floor against
  * the IEEE intrinsics (__fdiv_rn, F2I) on n pseudo-random operand triples; *mismatches must be 0. */
 int otslam_selftest_division(uint64_t n, uint64_t seed, uint64_t* mismatches, int device);
+
+/* device self-test of the parallel sequential-order FP64 accumulation (csrc/ordered_sum.cu) against
+ * the scalar left-to-right loop on n generated terms: totals and every prefix must agree bit for bit.
+ * pattern 0 = triangle-area-like, 1 = 2^-64..2^64 magnitudes, 2 = coarse grid (frequent exact ties),
+ * 3 = zeros and jumps, 4 = with negative / infinite terms. */
+int otslam_selftest_ordered_sum(int64_t n, uint64_t seed, int pattern, uint64_t* mismatches, int device);
 
 /* ---- volume life cycle: o3d.pipelines.integration.ScalableTSDFVolume(voxel_length, sdf_trunc,
  *      color_type) (3d_model/reconstruct_rgbd.py:79-83); volume_unit_resolution = 16,
@@ -120,6 +129,12 @@ int otslam_volume_halo_import(otslam_volume* v, int64_t n, const int32_t* keys, 
 int otslam_volume_extract_mesh(otslam_volume* v, int64_t* n_vertices, int64_t* n_faces);
 int otslam_volume_mesh_copy(otslam_volume* v, double* vertices, double* colors, double* normals, int32_t* faces,
                             int32_t* edge_keys);
+/* mesh.sample_points_uniformly(n) (reconstruct_rgbd_filter.py:123) straight from the mesh the last
+ * otslam_volume_extract_mesh left in HBM: no download + re-upload of the (often ~100 MB) mesh when the
+ * caller only wants the samples.  Same arithmetic and sample order as otslam_mesh_sample_uniform;
+ * out_colors / out_normals nullable. */
+int otslam_volume_mesh_sample(otslam_volume* v, int64_t n_samples, uint64_t seed, double* out_points,
+                              double* out_colors, double* out_normals);
 /* volume.extract_point_cloud() (named by north_star; zero crossings along +x/+y/+z) */
 int otslam_volume_extract_points(otslam_volume* v, int64_t* n_points);
 int otslam_volume_points_copy(otslam_volume* v, double* points, double* colors, int32_t* edge_keys);

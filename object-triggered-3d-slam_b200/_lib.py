@@ -34,7 +34,9 @@ _SIGS = {
     "otslam_version": (_i, []),
     "otslam_launch_count": (_i64, []),
     "otslam_last_op_device_ms": (_d, []),
+    "otslam_trim_scratch": (_i, []),
     "otslam_selftest_division": (_i, [_u64, _u64, C.POINTER(_u64), _i]),
+    "otslam_selftest_ordered_sum": (_i, [_i64, _u64, _i, C.POINTER(_u64), _i]),
     "otslam_volume_create": (_i, [_d, _d, _i, _i, C.POINTER(SlabSpec), C.POINTER(_vp)]),
     "otslam_volume_destroy": (_i, [_vp]),
     "otslam_volume_reset": (_i, [_vp]),
@@ -52,6 +54,7 @@ _SIGS = {
     "otslam_volume_halo_import": (_i, [_vp, _i64, _vp, _vp]),
     "otslam_volume_extract_mesh": (_i, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
     "otslam_volume_mesh_copy": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "otslam_volume_mesh_sample": (_i, [_vp, _i64, _u64, _vp, _vp, _vp]),
     "otslam_volume_extract_points": (_i, [_vp, C.POINTER(_i64)]),
     "otslam_volume_points_copy": (_i, [_vp, _vp, _vp, _vp]),
     "otslam_depth_convert": (_i, [_vp, _i64, _d, _d, _vp, _i]),

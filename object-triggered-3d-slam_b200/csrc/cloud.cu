@@ -176,71 +176,8 @@ __global__ void __launch_bounds__(256) tri_area_kernel(const double* __restrict_
     area[t] = __dmul_rn(0.5, __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(x0, x0), __dmul_rn(x1, x1)), __dmul_rn(x2, x2))));
 }
 
-// Sequential-order FP64 sum / prefix over n values (the reference's scalar accumulations:
-// `surface_area += area`, `cdf[t] = area[t]/total + cdf[t-1]`, the mean / sigma sums of the outlier
-// filter).  FP addition is not associative, so the adds MUST happen in index order: one warp streams
-// the array through shared memory in 1024-element stages (coalesced loads of the next stage are in
-// flight while the current one is consumed, element transforms are applied in parallel), and lane 0
-// walks each stage with the dependent DADD chain -- the only inherently serial part (~10 cycles per
-// element).  Bit-identical to the scalar loop.
-//   mode 0: out[0] = sum(x)                         mode 1: in-place inclusive prefix of x[i] / *div
-//   mode 2: out[0] = sum(x > 0 ? x : 0)             mode 3: out[0] = sum(x > 0 ? (x - mean)^2 : 0)
-constexpr int kOrdStage = 1024;
-__global__ void __launch_bounds__(32) ordered_accumulate_kernel(double* __restrict__ io, int64_t n, int mode, const double* __restrict__ div,
-                                                                double mean, double* __restrict__ out) {
-    __shared__ double buf[kOrdStage];
-    const int lane = threadIdx.x;
-    const double dv = (mode == 1) ? *div : 1.0;
-    double nxt[kOrdStage / 32];
-    auto load_stage = [&](int64_t base) {
-#pragma unroll
-        for (int k = 0; k < kOrdStage / 32; ++k) {
-            const int64_t i = base + k * 32 + lane;
-            nxt[k] = (i < n) ? io[i] : 0.0;
-        }
-    };
-    double acc = 0.0;
-    bool first = true;
-    load_stage(0);
-    for (int64_t base = 0; base < n; base += kOrdStage) {
-#pragma unroll
-        for (int k = 0; k < kOrdStage / 32; ++k) {
-            double v = nxt[k];
-            if (mode == 1) v = __ddiv_rn(v, dv);
-            else if (mode == 2) v = v > 0.0 ? v : 0.0;
-            else if (mode == 3) v = v > 0.0 ? __dmul_rn(__dsub_rn(v, mean), __dsub_rn(v, mean)) : 0.0;
-            buf[k * 32 + lane] = v;
-        }
-        if (base + kOrdStage < n) load_stage(base + kOrdStage);     // in flight during the serial walk
-        __syncwarp();
-        const int cnt = (int)min((int64_t)kOrdStage, n - base);
-        if (lane == 0) {
-            int j = 0;
-            if (first) { acc = buf[0]; if (mode == 1) buf[0] = acc; j = 1; first = false; }
-#pragma unroll 8
-            for (; j < cnt; ++j) {
-                acc = __dadd_rn(acc, buf[j]);
-                if (mode == 1) buf[j] = acc;
-            }
-        }
-        __syncwarp();
-        if (mode == 1) {
-#pragma unroll
-            for (int k = 0; k < kOrdStage / 32; ++k) {
-                const int64_t i = base + k * 32 + lane;
-                if (i < n) io[i] = buf[k * 32 + lane];
-            }
-        }
-        __syncwarp();
-    }
-    if (mode != 1 && lane == 0) out[0] = (n > 0) ? acc : 0.0;
-}
-
-int device_ordered_sum(double* d_x, int64_t n, int mode, const double* d_div, double mean, double* d_out, cudaStream_t s) {
-    ordered_accumulate_kernel<<<1, 32, 0, s>>>(d_x, n, mode, d_div, mean, d_out);
-    OT_LAUNCHED();
-    return OTSLAM_OK;
-}
+// ---- sequential-order accumulation (surface area, area CDF, outlier-filter statistics): ordered_sum.cu
+int device_ordered_sum(double* d_x, int64_t n, int mode, const double* d_div, double mean, double* d_out, cudaStream_t s);
 
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
     x += 0x9E3779B97F4A7C15ull;
@@ -434,6 +371,37 @@ int otslam_mesh_sample_uniform(const double* vertices, const double* colors, con
     OT_CUDA(cudaMemcpy(out_points, op.p, n_samples * 24, cudaMemcpyDeviceToHost));
     if (has_c) OT_CUDA(cudaMemcpy(out_colors, oc.p, n_samples * 24, cudaMemcpyDeviceToHost));
     if (has_n) OT_CUDA(cudaMemcpy(out_normals, on.p, n_samples * 24, cudaMemcpyDeviceToHost));
+    return OTSLAM_OK;
+}
+
+int otslam_volume_mesh_sample(otslam_volume* v, int64_t n_samples, uint64_t seed, double* out_points, double* out_colors,
+                              double* out_normals) {
+    if (!v) return set_error(OTSLAM_ERR_INVALID, "null volume");
+    if (n_samples <= 0) return set_error(OTSLAM_ERR_INVALID, "[SamplePointsUniformly] number_of_points <= 0");
+    const MeshResult& m = v->mesh;
+    if (m.nf <= 0 || m.nv <= 0) return set_error(OTSLAM_ERR_INVALID, "[SamplePointsUniformly] input mesh has no triangles");
+    if (!out_points) return set_error(OTSLAM_ERR_INVALID, "null output");
+    OT_TRY(use_device(v->device));
+    cudaStream_t s = v->stream;
+    DevBuf<double> area, total, op, oc, on;
+    OT_CUDA(area.alloc(m.nf)); OT_CUDA(total.alloc(1)); OT_CUDA(op.alloc(n_samples * 3));
+    if (out_colors) OT_CUDA(oc.alloc(n_samples * 3));
+    if (out_normals) OT_CUDA(on.alloc(n_samples * 3));
+    {
+        OpTimer timer(s);
+        tri_area_kernel<<<(unsigned)((m.nf + 255) / 256), 256, 0, s>>>(m.d_verts, m.d_faces, m.nf, area.p);
+        OT_LAUNCHED();
+        OT_TRY(device_ordered_sum(area.p, m.nf, 0, nullptr, 0.0, total.p, s));
+        OT_TRY(device_ordered_sum(area.p, m.nf, 1, total.p, 0.0, nullptr, s));
+        sample_kernel<<<(unsigned)((n_samples + 255) / 256), 256, 0, s>>>(m.d_verts, out_colors ? m.d_colors : nullptr,
+                                                                          out_normals ? m.d_normals : nullptr, m.d_faces, m.nf, area.p,
+                                                                          n_samples, seed, op.p, oc.p, on.p);
+        OT_LAUNCHED();
+    }
+    OT_CUDA(cudaMemcpyAsync(out_points, op.p, n_samples * 24, cudaMemcpyDeviceToHost, s));
+    if (out_colors) OT_CUDA(cudaMemcpyAsync(out_colors, oc.p, n_samples * 24, cudaMemcpyDeviceToHost, s));
+    if (out_normals) OT_CUDA(cudaMemcpyAsync(out_normals, on.p, n_samples * 24, cudaMemcpyDeviceToHost, s));
+    OT_CUDA(cudaStreamSynchronize(s));
     return OTSLAM_OK;
 }
 

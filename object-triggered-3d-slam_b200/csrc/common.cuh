@@ -15,8 +15,10 @@ extern thread_local std::string g_last_error;
 extern std::atomic<int64_t> g_launches;
 extern thread_local double g_last_op_ms;
 
+extern thread_local uint64_t g_error_count;
 inline int set_error(int code, const std::string& msg) {
     g_last_error = msg;
+    ++g_error_count;
     return code;
 }
 
@@ -139,16 +141,39 @@ __host__ __device__ inline bool slab_keeps(const SlabSpec& s, int kx, int ky, in
     return slab_owner(s, a) == s.rank || (s.halo && slab_owner(s, a - 1) == s.rank);
 }
 
-// simple RAII device buffer for the stateless operators
+// Scratch cache for the operators' temporaries and results: cudaMalloc / cudaFree cost 0.1-0.5 ms each
+// (and cudaFree synchronises the device), which dominated the post-stage operators (a dozen buffers
+// per call, kernels of a few hundred microseconds).  Freed blocks go to a per-device free list and
+// are handed out again to requests of similar size.  Every operator synchronises before it returns,
+// so a released block is idle -- except on an error return, which is why a release that follows an
+// error (the thread's error count moved since the allocation) drains the device first.
+// otslam_trim_scratch() releases the cache.
+extern thread_local uint64_t g_error_count;
+cudaError_t scratch_alloc(void** p, size_t bytes);
+void scratch_free(void* p);
+
+// RAII device buffer for the operators
 template <typename T>
 struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
-    ~DevBuf() { if (p) cudaFree(p); }
+    uint64_t err_epoch = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), err_epoch(o.err_epoch) { o.p = nullptr; o.n = 0; }
+    ~DevBuf() { release(); }
+    void release() {
+        if (!p) return;
+        if (err_epoch != g_error_count) cudaDeviceSynchronize();
+        scratch_free(p);
+        p = nullptr;
+    }
     cudaError_t alloc(size_t count) {
-        if (p) { cudaFree(p); p = nullptr; }
+        release();
         n = count;
-        return cudaMalloc((void**)&p, (count ? count : 1) * sizeof(T));
+        err_epoch = g_error_count;
+        return scratch_alloc((void**)&p, (count ? count : 1) * sizeof(T));
     }
 };
 

@@ -178,31 +178,8 @@ __global__ void __launch_bounds__(128) mc_count_kernel(const int32_t* __restrict
     if (t == 127) vcount[i] = base + inc;
 }
 
-// single-CTA exclusive scan (n up to a few million); total written to out[n]
-__global__ void __launch_bounds__(1024) scan_kernel(const int* __restrict__ in, int64_t* __restrict__ out, int n) {
-    __shared__ int64_t part[1024];
-    const int t = threadIdx.x;
-    const int per = (n + 1023) / 1024;
-    const int b = t * per, e = min(n, b + per);
-    int64_t s = 0;
-    for (int i = b; i < e; ++i) s += in[i];
-    part[t] = s;
-    __syncthreads();
-    if (t == 0) {
-        int64_t acc = 0;
-        for (int i = 0; i < 1024; ++i) { const int64_t v = part[i]; part[i] = acc; acc += v; }
-        out[n] = acc;
-    }
-    __syncthreads();
-    int64_t acc = part[t];
-    for (int i = b; i < e; ++i) { out[i] = acc; acc += in[i]; }
-}
-
-int device_exclusive_scan(const int* d_in, int64_t* d_out, int n, cudaStream_t s) {
-    scan_kernel<<<1, 1024, 0, s>>>(d_in, d_out, n);
-    OT_LAUNCHED();
-    return OTSLAM_OK;
-}
+// exclusive scan int32 -> int64 with the total at out[n]: scan.cu
+int device_exclusive_scan(const int* d_in, int64_t* d_out, int n, cudaStream_t s);
 
 __global__ void scatter_base_kernel(const int32_t* __restrict__ bslots, const int64_t* __restrict__ vbase, int n,
                                     int64_t* __restrict__ vbase_by_slot) {
@@ -325,35 +302,63 @@ __global__ void __launch_bounds__(256) mc_faces_kernel(ExtractCtx c, const uint3
     }
 }
 
-// ---- compute_vertex_normals
+// ---- compute_vertex_normals.  The reference adds each triangle's un-normalised normal to
+// its three vertices in one sequential loop over the triangles, so a vertex's sum is taken in
+// triangle-index order; FP64 atomics would make the low bits depend on the launch.  Here every vertex
+// gets the list of its corners (corner id = 3 * triangle + k): degree count -> scan -> fill (integer
+// atomics: the SET of a vertex's corners is deterministic, only its order in the list is not) -> one
+// thread per vertex sorts its short list and adds the face normals in ascending corner order.
+// Bit-identical to the scalar loop, and the same bits on every run.
 __global__ void __launch_bounds__(256) face_normals_kernel(const double* __restrict__ verts, const int32_t* __restrict__ faces,
-                                                           int64_t nf, double* __restrict__ normals) {
+                                                           int64_t nf, int64_t nv, double* __restrict__ fnrm, int* __restrict__ deg) {
     const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= nf) return;
     const int a = faces[3 * f], b = faces[3 * f + 1], cidx = faces[3 * f + 2];
+    if ((unsigned)a >= (unsigned)nv || (unsigned)b >= (unsigned)nv || (unsigned)cidx >= (unsigned)nv) return;   // malformed face: ignored
     double e1[3], e2[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         e1[k] = __dsub_rn(verts[3 * (size_t)b + k], verts[3 * (size_t)a + k]);
         e2[k] = __dsub_rn(verts[3 * (size_t)cidx + k], verts[3 * (size_t)a + k]);
     }
-    const double n[3] = {__dsub_rn(__dmul_rn(e1[1], e2[2]), __dmul_rn(e1[2], e2[1])),
-                         __dsub_rn(__dmul_rn(e1[2], e2[0]), __dmul_rn(e1[0], e2[2])),
-                         __dsub_rn(__dmul_rn(e1[0], e2[1]), __dmul_rn(e1[1], e2[0]))};
-    const int v[3] = {a, b, cidx};
-#pragma unroll
-    for (int j = 0; j < 3; ++j)
-#pragma unroll
-        for (int k = 0; k < 3; ++k) atomicAdd(normals + 3 * (size_t)v[j] + k, n[k]);
+    fnrm[3 * f] = __dsub_rn(__dmul_rn(e1[1], e2[2]), __dmul_rn(e1[2], e2[1]));
+    fnrm[3 * f + 1] = __dsub_rn(__dmul_rn(e1[2], e2[0]), __dmul_rn(e1[0], e2[2]));
+    fnrm[3 * f + 2] = __dsub_rn(__dmul_rn(e1[0], e2[1]), __dmul_rn(e1[1], e2[0]));
+    atomicAdd(deg + a, 1); atomicAdd(deg + b, 1); atomicAdd(deg + cidx, 1);
 }
 
-__global__ void __launch_bounds__(256) normalize_kernel(double* __restrict__ normals, int64_t nv) {
+__global__ void __launch_bounds__(256) corner_fill_kernel(const int32_t* __restrict__ faces, int64_t n_corners,
+                                                          int64_t nv, const int64_t* __restrict__ off, int* __restrict__ cursor,
+                                                          int32_t* __restrict__ adj) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_corners) return;
+    const int64_t f3 = c - c % 3;
+    if ((unsigned)faces[f3] >= (unsigned)nv || (unsigned)faces[f3 + 1] >= (unsigned)nv || (unsigned)faces[f3 + 2] >= (unsigned)nv) return;
+    const int v = faces[c];
+    adj[off[v] + atomicAdd(cursor + v, 1)] = (int32_t)c;
+}
+
+__global__ void __launch_bounds__(128) vertex_normals_kernel(int64_t nv, const int64_t* __restrict__ off, int32_t* __restrict__ adj,
+                                                             const double* __restrict__ fnrm, double* __restrict__ normals) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nv) return;
+    int32_t* a = adj + off[i];
+    const int d = (int)(off[i + 1] - off[i]);
+    for (int p = 1; p < d; ++p) {                 // insertion sort: degrees are ~6 on marching-cubes meshes
+        const int32_t x = a[p];
+        int q = p - 1;
+        for (; q >= 0 && a[q] > x; --q) a[q + 1] = a[q];
+        a[q + 1] = x;
+    }
+    double n0 = 0.0, n1 = 0.0, n2 = 0.0;
+    for (int p = 0; p < d; ++p) {
+        const double* f = fnrm + 3 * (size_t)(a[p] / 3);
+        n0 = __dadd_rn(n0, f[0]); n1 = __dadd_rn(n1, f[1]); n2 = __dadd_rn(n2, f[2]);
+    }
+    const double l = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(n0, n0), __dmul_rn(n1, n1)), __dmul_rn(n2, n2)));
     double* n = normals + 3 * i;
-    const double l = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(n[0], n[0]), __dmul_rn(n[1], n[1])), __dmul_rn(n[2], n[2])));
     if (l > 0.0) {
-        n[0] = __ddiv_rn(n[0], l); n[1] = __ddiv_rn(n[1], l); n[2] = __ddiv_rn(n[2], l);
+        n[0] = __ddiv_rn(n0, l); n[1] = __ddiv_rn(n1, l); n[2] = __ddiv_rn(n2, l);
     } else {
         n[0] = 0.0; n[1] = 0.0; n[2] = 1.0;
     }
@@ -362,12 +367,24 @@ __global__ void __launch_bounds__(256) normalize_kernel(double* __restrict__ nor
 int device_vertex_normals(const double* d_verts, int64_t nv, const int32_t* d_faces, int64_t nf, double* d_normals,
                           cudaStream_t s) {
     if (nv == 0) return OTSLAM_OK;
-    OT_CUDA(cudaMemsetAsync(d_normals, 0, (size_t)nv * 24, s));
+    if (nv > 0x7fffffffLL || 3 * nf > 0x7fffffffLL) return set_error(OTSLAM_ERR_OVERFLOW, "mesh exceeds int32 corner indices");
+    DevBuf<double> fnrm;
+    DevBuf<int> deg;                 // [2][nv]: degree, then the fill cursor
+    DevBuf<int64_t> off;
+    DevBuf<int32_t> adj;
+    OT_CUDA(fnrm.alloc((size_t)std::max<int64_t>(nf, 1) * 3)); OT_CUDA(deg.alloc((size_t)nv * 2)); OT_CUDA(off.alloc(nv + 1));
+    OT_CUDA(adj.alloc((size_t)std::max<int64_t>(nf, 1) * 3));
+    OT_CUDA(cudaMemsetAsync(deg.p, 0, (size_t)nv * 2 * sizeof(int), s));
     if (nf > 0) {
-        face_normals_kernel<<<(unsigned)((nf + 255) / 256), 256, 0, s>>>(d_verts, d_faces, nf, d_normals);
+        face_normals_kernel<<<(unsigned)((nf + 255) / 256), 256, 0, s>>>(d_verts, d_faces, nf, nv, fnrm.p, deg.p);
         OT_LAUNCHED();
     }
-    normalize_kernel<<<(unsigned)((nv + 255) / 256), 256, 0, s>>>(d_normals, nv);
+    OT_TRY(device_exclusive_scan(deg.p, off.p, (int)nv, s));
+    if (nf > 0) {
+        corner_fill_kernel<<<(unsigned)((3 * nf + 255) / 256), 256, 0, s>>>(d_faces, 3 * nf, nv, off.p, deg.p + nv, adj.p);
+        OT_LAUNCHED();
+    }
+    vertex_normals_kernel<<<(unsigned)((nv + 127) / 128), 128, 0, s>>>(nv, off.p, adj.p, fnrm.p, d_normals);
     OT_LAUNCHED();
     return OTSLAM_OK;
 }
@@ -517,10 +534,8 @@ int otslam_volume_extract_mesh(otslam_volume* v, int64_t* n_vertices, int64_t* n
     OT_LAUNCHED();
     mc_count_kernel<<<n, 128, 0, s>>>(c.bslots, flags.p, wprefix.p, vcount.p);
     OT_LAUNCHED();
-    scan_kernel<<<1, 1024, 0, s>>>(vcount.p, vbase.p, n);
-    OT_LAUNCHED();
-    scan_kernel<<<1, 1024, 0, s>>>(tri_count.p, fbase.p, n);
-    OT_LAUNCHED();
+    OT_TRY(device_exclusive_scan(vcount.p, vbase.p, n, s));
+    OT_TRY(device_exclusive_scan(tri_count.p, fbase.p, n, s));
     scatter_base_kernel<<<(n + 255) / 256, 256, 0, s>>>(c.bslots, vbase.p, n, vbase_slot.p);
     OT_LAUNCHED();
     int64_t nv = 0, nf = 0;
@@ -531,11 +546,11 @@ int otslam_volume_extract_mesh(otslam_volume* v, int64_t* n_vertices, int64_t* n
     MeshResult& m = v->mesh;
     m.nv = nv; m.nf = nf;
     if (nv > 0) {
-        OT_CUDA(cudaMalloc((void**)&m.d_verts, (size_t)nv * 24));
-        OT_CUDA(cudaMalloc((void**)&m.d_colors, (size_t)nv * 24));
-        OT_CUDA(cudaMalloc((void**)&m.d_normals, (size_t)nv * 24));
-        OT_CUDA(cudaMalloc((void**)&m.d_ekeys, (size_t)nv * 16));
-        OT_CUDA(cudaMalloc((void**)&m.d_faces, (size_t)std::max<int64_t>(nf, 1) * 12));
+        OT_CUDA(scratch_alloc((void**)&m.d_verts, (size_t)nv * 24));
+        OT_CUDA(scratch_alloc((void**)&m.d_colors, (size_t)nv * 24));
+        OT_CUDA(scratch_alloc((void**)&m.d_normals, (size_t)nv * 24));
+        OT_CUDA(scratch_alloc((void**)&m.d_ekeys, (size_t)nv * 16));
+        OT_CUDA(scratch_alloc((void**)&m.d_faces, (size_t)std::max<int64_t>(nf, 1) * 12));
         mc_vertices_kernel<<<n, 128, 0, s>>>(c, flags.p, wprefix.p, vbase.p, m.d_verts, m.d_colors, m.d_ekeys);
         OT_LAUNCHED();
         if (nf > 0) {
@@ -582,17 +597,16 @@ int otslam_volume_extract_points(otslam_volume* v, int64_t* n_points) {
     OT_CUDA(pcount.alloc(n)); OT_CUDA(pbase.alloc(n + 1));
     pc_extract_kernel<<<n, 256, 0, s>>>(c, nullptr, pcount.p, nullptr, nullptr, nullptr);
     OT_LAUNCHED();
-    scan_kernel<<<1, 1024, 0, s>>>(pcount.p, pbase.p, n);
-    OT_LAUNCHED();
+    OT_TRY(device_exclusive_scan(pcount.p, pbase.p, n, s));
     int64_t np = 0;
     OT_CUDA(cudaMemcpyAsync(&np, pbase.p + n, 8, cudaMemcpyDeviceToHost, s));
     OT_CUDA(cudaStreamSynchronize(s));
     PointsResult& p = v->points;
     p.n = np;
     if (np > 0) {
-        OT_CUDA(cudaMalloc((void**)&p.d_pts, (size_t)np * 24));
-        OT_CUDA(cudaMalloc((void**)&p.d_cols, (size_t)np * 24));
-        OT_CUDA(cudaMalloc((void**)&p.d_ekeys, (size_t)np * 16));
+        OT_CUDA(scratch_alloc((void**)&p.d_pts, (size_t)np * 24));
+        OT_CUDA(scratch_alloc((void**)&p.d_cols, (size_t)np * 24));
+        OT_CUDA(scratch_alloc((void**)&p.d_ekeys, (size_t)np * 16));
         pc_extract_kernel<<<n, 256, 0, s>>>(c, pbase.p, nullptr, p.d_pts, p.d_cols, p.d_ekeys);
         OT_LAUNCHED();
         OT_CUDA(cudaStreamSynchronize(s));

@@ -13,6 +13,8 @@
 // __match_any_sync ranking.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "volume.cuh"
@@ -170,7 +172,7 @@ __global__ void __launch_bounds__(256) radix_scatter_kernel(const uint64_t* __re
 
 // sorts by the low `bits` bits of the keys; result ends up in (k_out, v_out)
 static int sort_pairs(DevBuf<uint64_t>& k_in, DevBuf<int32_t>& v_in, DevBuf<uint64_t>& k_out, DevBuf<int32_t>& v_out, int64_t n,
-                      int bits = 63) {
+                      int bits) {
     const int n_cta = (int)((n + kSortTile - 1) / kSortTile);
     const int passes = std::max(1, (bits + 7) / 8);
     DevBuf<int> hist;
@@ -294,27 +296,47 @@ __global__ void __launch_bounds__(256) cell_hash_build_kernel(const uint64_t* __
     }
 }
 
+// one level of the search structure: points bucketed by uniform-grid cell (sorted by cell key), cell -> bucket hash
+struct KnnGrid {
+    const int32_t* idx;         // sorted position -> original index
+    const int32_t* seg_start;   // [n_seg+1]
+    const uint64_t* hkeys;
+    const int32_t* hvals;
+    uint32_t cap_mask;
+    double mn[3], cell;
+    int dim[3];
+    KeyLayout L;
+};
+
+// Two levels.  Scanned clouds are surfaces: a grid sized for ~2 points per cell of the bounding-box VOLUME
+// puts hundreds of points into every occupied cell (1 M points on a table: ~200), and each query then
+// computes thousands of distances for its 20 neighbours.  The fine level is sized from the measured
+// occupancy so that an occupied cell holds ~8 points and serves the first `fine_rings` rings; a query that
+// cannot finish there (outliers, sparse regions: ring r costs ~24 r^2 hash probes) restarts on the coarse
+// level, whose larger cells reach far with few rings; a query that is still searching after `coarse_rings`
+// rings there (an isolated point far from everything: ring r costs ~24 r^2 probes, and ONE such warp
+// crawling through 30 rings was 40 % of the kernel's duration) restarts on the top level (cells 8x larger).
+// The result is the exact k smallest squared distances on any level (conservative ring termination), so
+// it does not depend on the cell sizes.
 struct KnnArgs {
     const double* pts;          // target cloud, original order
     const double* qpts;         // query points (== pts for the outlier filter)
     const int32_t* qidx;        // query visit order -> query index (null: identity)
     int64_t nq;
     int mode;                   // 0: dbar = mean of the k sqrt distances (A.8); 1: nearest-neighbour distance
-    const int32_t* idx;         // sorted position -> original index
-    const int32_t* seg_start;   // [n_seg+1]
-    const uint64_t* hkeys;
-    const int32_t* hvals;
-    uint32_t cap_mask;
     int64_t n;
     int k;
-    double mn[3], cell;
-    int dim[3];
-    KeyLayout L;
+    int fine_rings;             // 0: no fine level
+    int coarse_rings;           // ring limit on the coarse level when a top level exists (else unlimited)
+    KnnGrid fine, coarse, top;
     double* dbar;               // [n] original order
 };
 
 constexpr int kKnnWarps = 8;
 constexpr int kKnnMaxK = 128;
+constexpr int kKnnTableRings = 3;                       // shells of rings 0..3: 1 + 26 + 98 + 218 = 343 cells
+__constant__ int c_shell_offsets[343];                  // dx | dy << 8 | dz << 16 (signed bytes), ring by ring
+__constant__ int c_shell_start[kKnnTableRings + 2];
 
 __device__ __forceinline__ void warp_argmax(const double* best, int cnt, int lane, double& vmax, int& pmax) {
     double v = -1.0;
@@ -331,40 +353,32 @@ __device__ __forceinline__ void warp_argmax(const double* best, int cnt, int lan
     vmax = v; pmax = p;
 }
 
-__global__ void __launch_bounds__(kKnnWarps * 32) knn_mean_dist_kernel(KnnArgs a) {
-    __shared__ double s_best[kKnnWarps][kKnnMaxK];
-    __shared__ double s_sorted[kKnnWarps][kKnnMaxK];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int64_t qpos = (int64_t)blockIdx.x * kKnnWarps + wid;
-    if (qpos >= a.nq) return;
-    double* best = s_best[wid];
-    double* sorted = s_sorted[wid];
-    const int64_t qi = a.qidx ? (int64_t)a.qidx[qpos] : qpos;
-    const double q[3] = {a.qpts[3 * (size_t)qi], a.qpts[3 * (size_t)qi + 1], a.qpts[3 * (size_t)qi + 2]};
+// ring search on one level; true when the k best are final (ring termination or whole grid covered),
+// false when `last_ring` was scanned without reaching that point
+__device__ __forceinline__ bool knn_search_level(const KnnGrid& g, const double* __restrict__ pts, const double (&q)[3], int k,
+                                                 int last_ring, int lane, double* best, double& reg_best, int& found, double& thr,
+                                                 int& pos) {
     int c[3];
 #pragma unroll
     for (int ax = 0; ax < 3; ++ax) {
-        const int v = (int)floor(__ddiv_rn(__dsub_rn(q[ax], a.mn[ax]), a.cell));
-        c[ax] = min(max(v, 0), a.dim[ax] - 1);
+        const int v = (int)floor(__ddiv_rn(__dsub_rn(q[ax], g.mn[ax]), g.cell));
+        c[ax] = min(max(v, 0), g.dim[ax] - 1);
     }
-    const int k = a.k;
-    int found = 0;
-    double thr = 0.0;   // current k-th best (valid when found == k)
-    int pos = 0;
-    const int maxring = max(a.dim[0], max(a.dim[1], a.dim[2]));
+    const int maxring = max(g.dim[0], max(g.dim[1], g.dim[2]));
     for (int ring = 0; ring <= maxring; ++ring) {
         if (found >= k && ring >= 1) {
             // distance from q to the nearest face of the already scanned box that still has grid behind it
             double reach = 1e300;
 #pragma unroll
             for (int ax = 0; ax < 3; ++ax) {
-                if (c[ax] - (ring - 1) > 0) reach = fmin(reach, q[ax] - (a.mn[ax] + (double)(c[ax] - (ring - 1)) * a.cell));
-                if (c[ax] + ring < a.dim[ax]) reach = fmin(reach, (a.mn[ax] + (double)(c[ax] + ring) * a.cell) - q[ax]);
+                if (c[ax] - (ring - 1) > 0) reach = fmin(reach, q[ax] - (g.mn[ax] + (double)(c[ax] - (ring - 1)) * g.cell));
+                if (c[ax] + ring < g.dim[ax]) reach = fmin(reach, (g.mn[ax] + (double)(c[ax] + ring) * g.cell) - q[ax]);
             }
-            if (reach == 1e300) break;                 // the box covers the whole grid
-            reach -= 1e-9 * a.cell;                    // conservative against rounding of the cell boundaries
-            if (reach > 0.0 && reach * reach > thr) break;
+            if (reach == 1e300) return true;           // the box covers the whole grid
+            reach -= 1e-9 * g.cell;                    // conservative against rounding of the cell boundaries
+            if (reach > 0.0 && reach * reach > thr) return true;
         }
+        if (ring > last_ring) return false;
         // enumerate the shell cells of this ring, 32 at a time (one hash lookup per lane)
         const int side = 2 * ring + 1;
         const int ncell = ring == 0 ? 1 : side * side * side - (side - 2) * (side - 2) * (side - 2);
@@ -373,8 +387,10 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_mean_dist_kernel(KnnArgs a
             int seg = -1;
             if (ci < ncell) {
                 int dx, dy, dz;
-                if (ring == 0) { dx = dy = dz = 0; }
-                else {
+                if (ring <= kKnnTableRings) {              // precomputed offsets: no integer divisions on the common path
+                    const int o = c_shell_offsets[c_shell_start[ring] + ci];
+                    dx = (int)(signed char)(o & 0xFF); dy = (int)(signed char)((o >> 8) & 0xFF); dz = (int)(signed char)((o >> 16) & 0xFF);
+                } else {
                     // shell = two full z-caps (side*side each) + side walls: (side-2) z-layers of a square ring (4*side-4)
                     const int cap = side * side;
                     if (ci < 2 * cap) {
@@ -392,14 +408,14 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_mean_dist_kernel(KnnArgs a
                     }
                 }
                 const int x = c[0] + dx, y = c[1] + dy, z = c[2] + dz;
-                if (x >= 0 && x < a.dim[0] && y >= 0 && y < a.dim[1] && z >= 0 && z < a.dim[2]) {
-                    const uint64_t key = layout_key(a.L, x, y, z);
-                    uint32_t h = hash_key(key) & a.cap_mask;
+                if (x >= 0 && x < g.dim[0] && y >= 0 && y < g.dim[1] && z >= 0 && z < g.dim[2]) {
+                    const uint64_t key = layout_key(g.L, x, y, z);
+                    uint32_t h = hash_key(key) & g.cap_mask;
                     for (;;) {
-                        const uint64_t hk = a.hkeys[h];
-                        if (hk == key) { seg = a.hvals[h]; break; }
+                        const uint64_t hk = g.hkeys[h];
+                        if (hk == key) { seg = g.hvals[h]; break; }
                         if (hk == kEmptyKey) break;
-                        h = (h + 1) & a.cap_mask;
+                        h = (h + 1) & g.cap_mask;
                     }
                 }
             }
@@ -408,38 +424,87 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_mean_dist_kernel(KnnArgs a
                 const int src = __ffs(have) - 1;
                 have &= have - 1;
                 const int sg = __shfl_sync(0xffffffffu, seg, src);
-                const int b = a.seg_start[sg], e = a.seg_start[sg + 1];
+                const int b = g.seg_start[sg], e = g.seg_start[sg + 1];
                 for (int j0 = b; j0 < e; j0 += 32) {
                     const int j = j0 + lane;
                     double d2 = 0.0;
                     bool cand = false;
                     if (j < e) {
-                        const size_t pi = (size_t)a.idx[j];
-                        const double dx = __dsub_rn(q[0], a.pts[3 * pi]), dy = __dsub_rn(q[1], a.pts[3 * pi + 1]),
-                                     dz = __dsub_rn(q[2], a.pts[3 * pi + 2]);
+                        const size_t pi = (size_t)g.idx[j];
+                        const double dx = __dsub_rn(q[0], pts[3 * pi]), dy = __dsub_rn(q[1], pts[3 * pi + 1]),
+                                     dz = __dsub_rn(q[2], pts[3 * pi + 2]);
                         d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
                         cand = true;
                     }
                     unsigned todo = __ballot_sync(0xffffffffu, cand && (found < k || d2 < thr));
-                    while (todo) {
-                        const int L = __ffs(todo) - 1;
-                        todo &= todo - 1;
-                        const double d = __shfl_sync(0xffffffffu, d2, L);
-                        if (found < k) {
-                            if (lane == 0) best[found] = d;
-                            ++found;
-                            __syncwarp();
-                            if (found == k) warp_argmax(best, k, lane, thr, pos);
-                        } else if (d < thr) {
-                            if (lane == 0) best[pos] = d;
-                            __syncwarp();
-                            warp_argmax(best, k, lane, thr, pos);
+                    if (k <= 32) {
+                        // k best kept sorted ascending, one per lane (lanes >= found hold +inf): an insert is a
+                        // ballot (rank of the newcomer), one shuffle (shift the tail up) and a select
+                        while (todo) {
+                            const int L = __ffs(todo) - 1;
+                            todo &= todo - 1;
+                            const double d = __shfl_sync(0xffffffffu, d2, L);
+                            if (found == k && !(d < thr)) continue;                      // warp-uniform
+                            const int rank = __popc(__ballot_sync(0xffffffffu, reg_best <= d));   // ties: after its equals
+                            const double up = __shfl_up_sync(0xffffffffu, reg_best, 1);
+                            if (lane == rank) reg_best = d;
+                            else if (lane > rank) reg_best = up;
+                            if (found < k) ++found;
+                            if (lane >= k) reg_best = INFINITY;
+                            if (found == k) thr = __shfl_sync(0xffffffffu, reg_best, k - 1);
+                        }
+                    } else {
+                        while (todo) {
+                            const int L = __ffs(todo) - 1;
+                            todo &= todo - 1;
+                            const double d = __shfl_sync(0xffffffffu, d2, L);
+                            if (found < k) {
+                                if (lane == 0) best[found] = d;
+                                ++found;
+                                __syncwarp();
+                                if (found == k) warp_argmax(best, k, lane, thr, pos);
+                            } else if (d < thr) {
+                                if (lane == 0) best[pos] = d;
+                                __syncwarp();
+                                warp_argmax(best, k, lane, thr, pos);
+                            }
                         }
                     }
                 }
             }
         }
     }
+    return true;
+}
+
+__global__ void __launch_bounds__(kKnnWarps * 32) knn_mean_dist_kernel(KnnArgs a) {
+    __shared__ double s_best[kKnnWarps][kKnnMaxK];
+    __shared__ double s_sorted[kKnnWarps][kKnnMaxK];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t qpos = (int64_t)blockIdx.x * kKnnWarps + wid;
+    if (qpos >= a.nq) return;
+    double* best = s_best[wid];
+    double* sorted = s_sorted[wid];
+    const int64_t qi = a.qidx ? (int64_t)a.qidx[qpos] : qpos;
+    const double q[3] = {a.qpts[3 * (size_t)qi], a.qpts[3 * (size_t)qi + 1], a.qpts[3 * (size_t)qi + 2]};
+    const int k = a.k;
+    int found = 0;
+    double thr = 0.0;   // current k-th best (valid when found == k)
+    int pos = 0;
+    double reg_best = INFINITY;                    // k <= 32: the sorted k best, one per lane
+    bool done = false;
+    if (a.fine_rings > 0) done = knn_search_level(a.fine, a.pts, q, k, a.fine_rings, lane, best, reg_best, found, thr, pos);
+    if (!done) {
+        found = 0; thr = 0.0; pos = 0; reg_best = INFINITY;   // restart: the coarse buckets contain the fine level's finds again
+        __syncwarp();
+        done = knn_search_level(a.coarse, a.pts, q, k, a.coarse_rings, lane, best, reg_best, found, thr, pos);
+    }
+    if (!done) {
+        found = 0; thr = 0.0; pos = 0; reg_best = INFINITY;
+        __syncwarp();
+        knn_search_level(a.top, a.pts, q, k, 0x3fffffff, lane, best, reg_best, found, thr, pos);
+    }
+    if (k <= 32 && lane < found) best[lane] = reg_best;
     __syncwarp();
     // ascending order, then the sequential sum of square roots
     for (int e = lane; e < found; e += 32) {
@@ -458,6 +523,136 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_mean_dist_kernel(KnnArgs a
         if (a.mode == 1) a.dbar[qi] = found > 0 ? __dsqrt_rn(sorted[0]) : -1.0;
         else a.dbar[qi] = found > 0 ? __ddiv_rn(s, (double)found) : -1.0;
     }
+}
+
+// sum over buckets of size^2: sum / n = the number of points sharing a cell with a typical point
+__global__ void __launch_bounds__(256) crowding_kernel(const int32_t* __restrict__ seg_start, int64_t n_seg, unsigned long long* out) {
+    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long v = 0;
+    if (m < n_seg) { const unsigned long long c = (unsigned long long)(seg_start[m + 1] - seg_start[m]); v = c * c; }
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(out, v);
+}
+
+static int upload_shell_table() {
+    static bool done[64] = {};
+    int dev = 0;
+    OT_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && done[dev]) return OTSLAM_OK;
+    std::vector<int> off, start;
+    for (int ring = 0; ring <= kKnnTableRings; ++ring) {
+        start.push_back((int)off.size());
+        const int side = 2 * ring + 1;
+        const int ncell = ring == 0 ? 1 : side * side * side - (side - 2) * (side - 2) * (side - 2);
+        for (int ci = 0; ci < ncell; ++ci) {          // the kernel's arithmetic enumeration, verbatim
+            int dx, dy, dz;
+            if (ring == 0) { dx = dy = dz = 0; }
+            else {
+                const int cap = side * side;
+                if (ci < 2 * cap) {
+                    const int w = ci % cap;
+                    dz = (ci < cap) ? -ring : ring;
+                    dx = w / side - ring; dy = w % side - ring;
+                } else {
+                    const int r = ci - 2 * cap, per = 4 * side - 4;
+                    dz = r / per - ring + 1;
+                    const int w = r % per;
+                    if (w < side) { dx = -ring; dy = w - ring; }
+                    else if (w < 2 * side) { dx = ring; dy = w - side - ring; }
+                    else if (w < 3 * side - 2) { dy = -ring; dx = w - 2 * side - ring + 1; }
+                    else { dy = ring; dx = w - (3 * side - 2) - ring + 1; }
+                }
+            }
+            off.push_back((dx & 0xFF) | ((dy & 0xFF) << 8) | ((dz & 0xFF) << 16));
+        }
+    }
+    start.push_back((int)off.size());
+    if (off.size() != 343) return set_error(OTSLAM_ERR_INVALID, "shell table size");
+    OT_CUDA(cudaMemcpyToSymbol(c_shell_offsets, off.data(), off.size() * sizeof(int)));
+    OT_CUDA(cudaMemcpyToSymbol(c_shell_start, start.data(), start.size() * sizeof(int)));
+    if (dev >= 0 && dev < 64) done[dev] = true;
+    return OTSLAM_OK;
+}
+
+// ---- host side of the search structure
+struct GridBuffers {
+    DevBuf<uint64_t> k0, k1, hk;
+    DevBuf<int32_t> i0, i1, seg, hv;
+    int64_t n_seg = 0;
+};
+
+static int sort_pairs(DevBuf<uint64_t>& k_in, DevBuf<int32_t>& v_in, DevBuf<uint64_t>& k_out, DevBuf<int32_t>& v_out, int64_t n, int bits);
+static int find_segments(const uint64_t* d_keys, int64_t n, DevBuf<int32_t>& seg_start, int64_t* n_seg);
+
+// bucket the n points of d_pts on a grid of `cell`-sized cells over [mn, mx] (at most max_dim cells per axis)
+static int build_grid(const double* d_pts, int64_t n, const double mn[3], const double mx[3], double cell, int max_dim, GridBuffers& b,
+                      KnnGrid& g) {
+    const double ext[3] = {mx[0] - mn[0], mx[1] - mn[1], mx[2] - mn[2]};
+    const double maxext = std::max(ext[0], std::max(ext[1], ext[2]));
+    cell = std::max(cell, maxext / (double)max_dim);
+    if (!(cell > 0.0) || !std::isfinite(cell)) cell = 1.0;
+    g.cell = cell;
+    for (int ax = 0; ax < 3; ++ax) { g.mn[ax] = mn[ax]; g.dim[ax] = std::max(1, (int)std::floor(ext[ax] / cell) + 1); }
+    g.L = make_layout(g.dim[0], g.dim[1], g.dim[2]);
+    OT_CUDA(b.k0.alloc(n)); OT_CUDA(b.k1.alloc(n)); OT_CUDA(b.i0.alloc(n)); OT_CUDA(b.i1.alloc(n));
+    cell_key_kernel<<<(unsigned)((n + 255) / 256), 256>>>(d_pts, n, mn[0], mn[1], mn[2], cell, g.dim[0] - 1, g.dim[1] - 1, g.dim[2] - 1,
+                                                         g.L, b.k0.p, b.i0.p);
+    OT_LAUNCHED();
+    OT_TRY(sort_pairs(b.k0, b.i0, b.k1, b.i1, n, g.L.bits));
+    OT_TRY(find_segments(b.k1.p, n, b.seg, &b.n_seg));
+    uint32_t cap = 1024;
+    while ((int64_t)cap < 2 * b.n_seg) cap <<= 1;
+    OT_CUDA(b.hk.alloc(cap)); OT_CUDA(b.hv.alloc(cap));
+    OT_CUDA(cudaMemset(b.hk.p, 0xFF, (size_t)cap * 8));
+    cell_hash_build_kernel<<<(unsigned)((b.n_seg + 255) / 256), 256>>>(b.k1.p, b.seg.p, b.n_seg, b.hk.p, b.hv.p, cap - 1);
+    OT_LAUNCHED();
+    g.idx = b.i1.p; g.seg_start = b.seg.p; g.hkeys = b.hk.p; g.hvals = b.hv.p; g.cap_mask = cap - 1;
+    return OTSLAM_OK;
+}
+
+constexpr double kKnnFineOccupancy = 16.0;    // target points per occupied fine cell (measured best of 4..64 on 1 M surface points, k = 20)
+constexpr int kKnnFineRings = 3;
+
+// coarse level (~2 points per cell of the bounding-box volume) + fine level when the occupied cells are crowded
+constexpr int kKnnCoarseRings = 6;
+constexpr double kKnnTopFactor = 8.0;
+
+static int build_search(const double* d_pts, int64_t n, GridBuffers& bc, GridBuffers& bf, GridBuffers& bt, KnnArgs& a) {
+    double mn[3], mx[3];
+    OT_TRY(cloud_minmax(d_pts, n, mn, mx));
+    const double ext[3] = {mx[0] - mn[0], mx[1] - mn[1], mx[2] - mn[2]};
+    const double vol = std::max(ext[0], 1e-9) * std::max(ext[1], 1e-9) * std::max(ext[2], 1e-9);
+    const double cell = std::cbrt(vol / std::max(1.0, (double)n / 2.0));
+    OT_TRY(build_grid(d_pts, n, mn, mx, cell, 1024, bc, a.coarse));
+    a.coarse_rings = 0x3fffffff;
+    if (std::max(a.coarse.dim[0], std::max(a.coarse.dim[1], a.coarse.dim[2])) > 4 * kKnnCoarseRings) {
+        OT_TRY(build_grid(d_pts, n, mn, mx, a.coarse.cell * kKnnTopFactor, 1024, bt, a.top));
+        a.coarse_rings = kKnnCoarseRings;
+    }
+    OT_TRY(upload_shell_table());
+    a.fine_rings = 0;
+    // crowding seen by a typical point (mean bucket size weighted by the points in it); isolated outliers,
+    // which open many near-empty cells, do not dilute it the way n / n_cells would
+    DevBuf<unsigned long long> sq;
+    OT_CUDA(sq.alloc(1));
+    OT_CUDA(cudaMemset(sq.p, 0, 8));
+    crowding_kernel<<<(unsigned)((bc.n_seg + 255) / 256), 256>>>(bc.seg.p, bc.n_seg, sq.p);
+    OT_LAUNCHED();
+    unsigned long long hsq = 0;
+    OT_CUDA(cudaMemcpy(&hsq, sq.p, 8, cudaMemcpyDeviceToHost));
+    const double occ = (double)hsq / (double)n;
+    static const double target = getenv("OTSLAM_KNN_OCC") ? atof(getenv("OTSLAM_KNN_OCC")) : kKnnFineOccupancy;   // dev knobs
+    static const int rings = getenv("OTSLAM_KNN_RINGS") ? atoi(getenv("OTSLAM_KNN_RINGS")) : kKnnFineRings;
+    if (occ > 2.0 * target && rings > 0) {
+        // surface-like data: points per occupied cell scale with cell^2
+        const double fine_cell = a.coarse.cell * std::sqrt(target / occ);
+        OT_TRY(build_grid(d_pts, n, mn, mx, fine_cell, 1 << 16, bf, a.fine));
+        a.fine_rings = std::min(rings, kKnnTableRings);
+        if (getenv("OTSLAM_KNN_DEBUG"))
+            fprintf(stderr, "knn: n %lld coarse cell %.4g (%lld cells, crowding %.1f) fine cell %.4g (%lld cells)\n", (long long)n,
+                    a.coarse.cell, (long long)bc.n_seg, occ, a.fine.cell, (long long)bf.n_seg);
+    }
+    return OTSLAM_OK;
 }
 
 // sequential-order sums for the global mean / sigma: cloud.cu's ordered accumulation, modes 2 and 3
@@ -567,39 +762,12 @@ int otslam_cloud_remove_statistical_outlier(const double* points, int64_t n, int
     OT_CUDA(cudaMemcpy(dp.p, points, n * 24, cudaMemcpyHostToDevice));
     OpTimer timer;
     KnnArgs a;
-    double mx[3];
-    OT_TRY(cloud_minmax(dp.p, n, a.mn, mx));
-    // uniform grid: ~2 points per cell of the bounding box volume, at most 1024 cells per axis
-    const double ext[3] = {mx[0] - a.mn[0], mx[1] - a.mn[1], mx[2] - a.mn[2]};
-    const double vol = std::max(ext[0], 1e-9) * std::max(ext[1], 1e-9) * std::max(ext[2], 1e-9);
-    double cell = std::cbrt(vol / std::max(1.0, (double)n / 2.0));
-    const double maxext = std::max(ext[0], std::max(ext[1], ext[2]));
-    cell = std::max(cell, maxext / 1024.0);
-    if (!(cell > 0.0) || !std::isfinite(cell)) cell = 1.0;
-    a.cell = cell;
-    for (int ax = 0; ax < 3; ++ax) a.dim[ax] = std::max(1, (int)std::floor(ext[ax] / cell) + 1);
-    DevBuf<uint64_t> k0, k1;
-    DevBuf<int32_t> i0, i1;
-    OT_CUDA(k0.alloc(n)); OT_CUDA(k1.alloc(n)); OT_CUDA(i0.alloc(n)); OT_CUDA(i1.alloc(n));
-    a.L = make_layout(a.dim[0], a.dim[1], a.dim[2]);
-    cell_key_kernel<<<(unsigned)((n + 255) / 256), 256>>>(dp.p, n, a.mn[0], a.mn[1], a.mn[2], cell, a.dim[0] - 1, a.dim[1] - 1,
-                                                         a.dim[2] - 1, a.L, k0.p, i0.p);
-    OT_LAUNCHED();
-    OT_TRY(sort_pairs(k0, i0, k1, i1, n, a.L.bits));
-    DevBuf<int32_t> seg;
-    int64_t n_seg = 0;
-    OT_TRY(find_segments(k1.p, n, seg, &n_seg));
-    uint32_t cap = 1024;
-    while ((int64_t)cap < 2 * n_seg) cap <<= 1;
-    DevBuf<uint64_t> hk;
-    DevBuf<int32_t> hv;
-    OT_CUDA(hk.alloc(cap)); OT_CUDA(hv.alloc(cap));
-    OT_CUDA(cudaMemset(hk.p, 0xFF, (size_t)cap * 8));
-    cell_hash_build_kernel<<<(unsigned)((n_seg + 255) / 256), 256>>>(k1.p, seg.p, n_seg, hk.p, hv.p, cap - 1);
-    OT_LAUNCHED();
+    GridBuffers bc, bf, bt;
+    OT_TRY(build_search(dp.p, n, bc, bf, bt, a));
     DevBuf<double> dbar, scal;
     OT_CUDA(dbar.alloc(n)); OT_CUDA(scal.alloc(1));
-    a.pts = dp.p; a.qpts = dp.p; a.qidx = i1.p; a.nq = n; a.mode = 0; a.idx = i1.p; a.seg_start = seg.p; a.hkeys = hk.p; a.hvals = hv.p; a.cap_mask = cap - 1; a.n = n; a.k = k; a.dbar = dbar.p;
+    a.pts = dp.p; a.qpts = dp.p; a.qidx = a.fine_rings ? a.fine.idx : a.coarse.idx;   // visit queries cell by cell: neighbours share cache lines
+    a.nq = n; a.mode = 0; a.n = n; a.k = k; a.dbar = dbar.p;
     knn_mean_dist_kernel<<<(unsigned)((n + kKnnWarps - 1) / kKnnWarps), kKnnWarps * 32>>>(a);
     OT_LAUNCHED();
     if (mean_dist) OT_CUDA(cudaMemcpy(mean_dist, dbar.p, n * 8, cudaMemcpyDeviceToHost));
@@ -646,36 +814,9 @@ int otslam_cloud_nn_distance(const double* source, int64_t n_source, const doubl
     OT_CUDA(cudaMemcpy(dsrc.p, source, n_source * 24, cudaMemcpyHostToDevice));
     OpTimer timer;
     KnnArgs a;
-    double mx[3];
-    OT_TRY(cloud_minmax(dt.p, n_target, a.mn, mx));
-    const double ext[3] = {mx[0] - a.mn[0], mx[1] - a.mn[1], mx[2] - a.mn[2]};
-    const double vol = std::max(ext[0], 1e-9) * std::max(ext[1], 1e-9) * std::max(ext[2], 1e-9);
-    double cell = std::cbrt(vol / std::max(1.0, (double)n_target / 2.0));
-    cell = std::max(cell, std::max(ext[0], std::max(ext[1], ext[2])) / 1024.0);
-    if (!(cell > 0.0) || !std::isfinite(cell)) cell = 1.0;
-    a.cell = cell;
-    for (int ax = 0; ax < 3; ++ax) a.dim[ax] = std::max(1, (int)std::floor(ext[ax] / cell) + 1);
-    a.L = make_layout(a.dim[0], a.dim[1], a.dim[2]);
-    DevBuf<uint64_t> k0, k1;
-    DevBuf<int32_t> i0, i1;
-    OT_CUDA(k0.alloc(n_target)); OT_CUDA(k1.alloc(n_target)); OT_CUDA(i0.alloc(n_target)); OT_CUDA(i1.alloc(n_target));
-    cell_key_kernel<<<(unsigned)((n_target + 255) / 256), 256>>>(dt.p, n_target, a.mn[0], a.mn[1], a.mn[2], cell, a.dim[0] - 1,
-                                                                a.dim[1] - 1, a.dim[2] - 1, a.L, k0.p, i0.p);
-    OT_LAUNCHED();
-    OT_TRY(sort_pairs(k0, i0, k1, i1, n_target, a.L.bits));
-    DevBuf<int32_t> seg;
-    int64_t n_seg = 0;
-    OT_TRY(find_segments(k1.p, n_target, seg, &n_seg));
-    uint32_t cap = 1024;
-    while ((int64_t)cap < 2 * n_seg) cap <<= 1;
-    DevBuf<uint64_t> hk;
-    DevBuf<int32_t> hv;
-    OT_CUDA(hk.alloc(cap)); OT_CUDA(hv.alloc(cap));
-    OT_CUDA(cudaMemset(hk.p, 0xFF, (size_t)cap * 8));
-    cell_hash_build_kernel<<<(unsigned)((n_seg + 255) / 256), 256>>>(k1.p, seg.p, n_seg, hk.p, hv.p, cap - 1);
-    OT_LAUNCHED();
-    a.pts = dt.p; a.qpts = dsrc.p; a.qidx = nullptr; a.nq = n_source; a.mode = 1; a.idx = i1.p; a.seg_start = seg.p;
-    a.hkeys = hk.p; a.hvals = hv.p; a.cap_mask = cap - 1; a.n = n_target; a.k = 1; a.dbar = dout.p;
+    GridBuffers bc, bf, bt;
+    OT_TRY(build_search(dt.p, n_target, bc, bf, bt, a));
+    a.pts = dt.p; a.qpts = dsrc.p; a.qidx = nullptr; a.nq = n_source; a.mode = 1; a.n = n_target; a.k = 1; a.dbar = dout.p;
     knn_mean_dist_kernel<<<(unsigned)((n_source + kKnnWarps - 1) / kKnnWarps), kKnnWarps * 32>>>(a);
     OT_LAUNCHED();
     timer.stop();

@@ -245,38 +245,104 @@ class PointCloud:
         return self.select_by_index(idx), idx.tolist()
 
 
+class _ResidentArray:
+    """Stand-in for a mesh array that still lives in HBM (what Open3D exposes as a Vector3dVector):
+    len() is free, anything that needs the values (np.asarray, indexing, .shape ...) downloads the mesh."""
+
+    def __init__(self, mesh, name, n):
+        self._mesh, self._name, self._n = mesh, name, n
+
+    def __len__(self):
+        return self._n
+
+    def _host(self):
+        self._mesh._materialize()
+        return getattr(self._mesh, "_" + self._name)
+
+    def __array__(self, dtype=None, copy=None):
+        a = self._host()
+        return a if dtype is None else a.astype(dtype)
+
+    def __getitem__(self, i):
+        return self._host()[i]
+
+    def __iter__(self):
+        return iter(self._host())
+
+    def __getattr__(self, k):
+        if k.startswith("__"):
+            raise AttributeError(k)
+        return getattr(self._host(), k)
+
+
 class TriangleMesh:
     def __init__(self):
         self._vertices = np.zeros((0, 3), np.float64)
         self._vertex_colors = np.zeros((0, 3), np.float64)
         self._vertex_normals = np.zeros((0, 3), np.float64)
         self._triangles = np.zeros((0, 3), np.int32)
+        self._res = None          # (TSDFVolume, nv, nf, has_colors) while the arrays are still in HBM
+        self._res_normals = False  # compute_vertex_normals() was called on the resident mesh
 
-    vertices = property(lambda s: s._vertices, lambda s, v: setattr(s, "_vertices", _as_n3(v)))
-    vertex_colors = property(lambda s: s._vertex_colors, lambda s, v: setattr(s, "_vertex_colors", _as_n3(v)))
-    vertex_normals = property(lambda s: s._vertex_normals, lambda s, v: setattr(s, "_vertex_normals", _as_n3(v)))
-    triangles = property(lambda s: s._triangles, lambda s, v: setattr(s, "_triangles", _as_n3(v, np.int32)))
+    # ---- device-resident state (set by ScalableTSDFVolume.extract_triangle_mesh) ---------------
+    def _attach_resident(self, vol, nv, nf, colors):
+        self._res = (vol, nv, nf, colors) if nv > 0 else None
+        self._res_normals = False
+
+    def _materialize(self):
+        """Download the resident arrays (once) and become an ordinary host mesh."""
+        if self._res is None:
+            return
+        vol, nv, nf, colors = self._res
+        self._res = None
+        v, c, n, f = vol.mesh_download(nv, nf, normals=self._res_normals)
+        self._vertices, self._triangles = v, f
+        if colors:
+            self._vertex_colors = c
+        if self._res_normals:
+            self._vertex_normals = n
+
+    def _get(self, name, present=True):
+        if self._res is not None:
+            nv, nf = self._res[1], self._res[2]
+            if not present:
+                return np.zeros((0, 3), np.float64)
+            return _ResidentArray(self, name, nf if name == "triangles" else nv)
+        return getattr(self, "_" + name)
+
+    def _set(self, name, value, dtype=np.float64):
+        self._materialize()
+        setattr(self, "_" + name, _as_n3(value, dtype))
+
+    vertices = property(lambda s: s._get("vertices"), lambda s, v: s._set("vertices", v))
+    vertex_colors = property(lambda s: s._get("vertex_colors", s._res is None or s._res[3]), lambda s, v: s._set("vertex_colors", v))
+    vertex_normals = property(lambda s: s._get("vertex_normals", s._res is None or s._res_normals),
+                              lambda s, v: s._set("vertex_normals", v))
+    triangles = property(lambda s: s._get("triangles"), lambda s, v: s._set("triangles", v, np.int32))
 
     def has_vertices(self):
-        return len(self._vertices) > 0
+        return len(self.vertices) > 0
 
     def has_triangles(self):
-        return len(self._vertices) > 0 and len(self._triangles) > 0
+        return len(self.vertices) > 0 and len(self.triangles) > 0
 
     def has_vertex_colors(self):
-        return len(self._vertices) > 0 and len(self._vertex_colors) == len(self._vertices)
+        return len(self.vertices) > 0 and len(self.vertex_colors) == len(self.vertices)
 
     def has_vertex_normals(self):
-        return len(self._vertices) > 0 and len(self._vertex_normals) == len(self._vertices)
+        return len(self.vertices) > 0 and len(self.vertex_normals) == len(self.vertices)
 
     def is_empty(self):
         return not self.has_vertices()
 
     def __repr__(self):
-        return f"TriangleMesh with {len(self._vertices)} points and {len(self._triangles)} triangles."
+        return f"TriangleMesh with {len(self.vertices)} points and {len(self.triangles)} triangles."
 
     def compute_vertex_normals(self, normalized=True):
         """reconstruct_rgbd.py:113."""
+        if self._res is not None:           # extraction already left the normals next to the mesh in HBM
+            self._res_normals = True
+            return self
         nv, nf = len(self._vertices), len(self._triangles)
         out = np.empty((nv, 3), np.float64)
         _lib.check(_lib.lib.otslam_mesh_vertex_normals(_lib.ptr(self._vertices), nv, _lib.ptr(self._triangles), nf, _lib.ptr(out), 0))
@@ -291,6 +357,15 @@ class TriangleMesh:
             raise RuntimeError("[SamplePointsUniformly] input mesh has no triangles")
         n = int(number_of_points)
         hc, hn = self.has_vertex_colors(), self.has_vertex_normals()
+        if self._res is not None:           # sample straight from HBM
+            op, oc, on = self._res[0].mesh_sample(n, _next_seed(seed), colors=hc, normals=hn)
+            pc = PointCloud()
+            pc._points = op
+            if hc:
+                pc._colors = oc
+            if hn:
+                pc._normals = on
+            return pc
         op = np.empty((n, 3), np.float64)
         oc = np.empty((n, 3), np.float64) if hc else None
         on = np.empty((n, 3), np.float64) if hn else None

@@ -57,11 +57,12 @@ class ScalableTSDFVolume:
             raise RuntimeError(_FMT)
 
     def extract_triangle_mesh(self):
-        v, c, n, f, _ = self._vol.extract_triangle_mesh(normals=False)
+        """reconstruct_rgbd.py:112.  The mesh (often ~100 MB) stays in HBM: the returned TriangleMesh
+        downloads its arrays only when they are read (np.asarray(mesh.vertices), write_triangle_mesh);
+        len(mesh.vertices), compute_vertex_normals() and sample_points_uniformly() work on the device."""
         m = geometry.TriangleMesh()
-        m.vertices, m.triangles = v, f
-        if self.color_type != TSDFVolumeColorType.NoColor:
-            m.vertex_colors = c
+        nv, nf = self._vol.extract_mesh_resident(owner=m)
+        m._attach_resident(self._vol, nv, nf, colors=self.color_type != TSDFVolumeColorType.NoColor)
         return m
 
     def extract_point_cloud(self):

@@ -4,6 +4,7 @@ Mirrors o3d.pipelines.integration.ScalableTSDFVolume as used at
 /root/reference/3d_model/reconstruct_rgbd.py:79-83,107,112.
 """
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -25,13 +26,56 @@ class TSDFVolume:
 
     def close(self):
         if getattr(self, "_h", None):
+            self._detach_resident_mesh()
             _lib.lib.otslam_volume_destroy(self._h)
             self._h = None
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:       # noqa: BLE001 -- interpreter shutdown
+            pass
 
     def reset(self):
+        self._detach_resident_mesh()
         _lib.check(_lib.lib.otslam_volume_reset(self._h))
+
+    # ---- the extracted mesh stays in HBM; a compat TriangleMesh may refer to it lazily ------------
+    def _detach_resident_mesh(self):
+        """The resident mesh is about to be replaced / freed: a lazy TriangleMesh still pointing at it
+        downloads its arrays first."""
+        ref = getattr(self, "_lazy_mesh", None)
+        self._lazy_mesh = None
+        m = ref() if ref is not None else None
+        if m is not None:
+            m._materialize()
+
+    def extract_mesh_resident(self, owner=None):
+        """extract_triangle_mesh + compute_vertex_normals on the device, result left in HBM.
+        Returns (n_vertices, n_faces); `owner` (a lazy TriangleMesh) is told before the result dies."""
+        self._detach_resident_mesh()
+        nv, nf = C.c_int64(0), C.c_int64(0)
+        _lib.check(_lib.lib.otslam_volume_extract_mesh(self._h, C.byref(nv), C.byref(nf)))
+        if owner is not None:
+            self._lazy_mesh = weakref.ref(owner)
+        return nv.value, nf.value
+
+    def mesh_download(self, nv, nf, normals=True):
+        verts = np.empty((nv, 3), np.float64)
+        cols = np.empty((nv, 3), np.float64)
+        nrm = np.empty((nv, 3), np.float64) if normals else None
+        faces = np.empty((nf, 3), np.int32)
+        _lib.check(_lib.lib.otslam_volume_mesh_copy(self._h, _lib.ptr(verts), _lib.ptr(cols), _lib.ptr(nrm), _lib.ptr(faces), None))
+        return verts, cols, nrm, faces
+
+    def mesh_sample(self, n, seed, colors=True, normals=False):
+        """sample_points_uniformly straight from the resident mesh (no mesh download / re-upload)."""
+        op = np.empty((n, 3), np.float64)
+        oc = np.empty((n, 3), np.float64) if colors else None
+        on = np.empty((n, 3), np.float64) if normals else None
+        _lib.check(_lib.lib.otslam_volume_mesh_sample(self._h, int(n), C.c_uint64(int(seed) & 0xFFFFFFFFFFFFFFFF), _lib.ptr(op),
+                                                      _lib.ptr(oc), _lib.ptr(on)))
+        return op, oc, on
 
     def set_stream(self, cuda_stream):
         _lib.check(_lib.lib.otslam_volume_set_stream(self._h, C.c_void_p(int(cuda_stream) if cuda_stream else 0)))
@@ -130,6 +174,7 @@ class TSDFVolume:
         _lib.check(_lib.lib.otslam_volume_halo_import(self._h, len(keys), _lib.ptr(keys), _lib.ptr(planes)))
 
     def extract_triangle_mesh(self, normals=True):
+        self._detach_resident_mesh()
         nv, nf = C.c_int64(0), C.c_int64(0)
         _lib.check(_lib.lib.otslam_volume_extract_mesh(self._h, C.byref(nv), C.byref(nf)))
         verts = np.empty((nv.value, 3), np.float64)

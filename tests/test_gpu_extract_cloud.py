@@ -38,7 +38,7 @@ def test_mesh_and_points_parity(table_seq, slab):
     assert (A[2] == B[2]).all()                                  # same triangles, same winding
     d1 = cKDTree(overts).query(gverts)[0].mean() + cKDTree(gverts).query(overts)[0].mean()
     assert d1 <= 0.25 * vl
-    assert np.abs(oracle.vertex_normals(gverts, gfaces) - gnrm).max() < 1e-9
+    assert (oracle.vertex_normals(gverts, gfaces) == gnrm).all()      # summed in triangle order: bit-exact
     gp, gc, gpe = gv.extract_point_cloud()
     op, oc, ope = ov.extract_point_cloud()
     a, b = lexorder(ope), lexorder(gpe)
@@ -135,7 +135,7 @@ def test_vertex_normals_and_sampling(mesh):
     m = o3d.geometry.TriangleMesh()
     m.vertices, m.vertex_colors, m.triangles = v, col, f
     m.compute_vertex_normals()
-    assert np.abs(m.vertex_normals - n).max() < 1e-9
+    assert (np.asarray(m.vertex_normals) == n).all()
     m.vertex_normals = n
     pc = m.sample_points_uniformly(number_of_points=100000, seed=11)
     op, oc, on, tri = oracle.sample_uniform(v, col, n, f, 100000, seed=11)
