@@ -205,74 +205,78 @@ __global__ void __launch_bounds__(256) os_quantise_kernel(const double* __restri
     if (lane == 0) { ce[c] = irregular ? kOsComplex : e; cK[c] = K; }
 }
 
-// ---- (C) exact carry propagation, one warp
-constexpr int kOsTile = 1024;
+// ---- (C) exact carry propagation, one warp.  32 chunks per step: within a run of simple chunks that
+// share the accumulator's binade the recurrence is an integer prefix sum (m_j = m + K_0 + ... + K_j, all
+// K >= 0), so the warp scans the 32 K's with shuffles, finds the first chunk that breaks the run (complex
+// flag, other predicted binade, or m_j > 2^53) with one ballot, commits every chunk before it at once and
+// replays only that chunk with the scalar chain.
 __global__ void __launch_bounds__(32) os_carry_kernel(double* __restrict__ io, int64_t n, int mode, const double* __restrict__ div, double mean,
                                                       const int* __restrict__ ce, const long long* __restrict__ cK, int64_t n_chunks,
                                                       double* __restrict__ carry_in, unsigned char* __restrict__ replayed,
                                                       double* __restrict__ out) {
-    __shared__ int se[kOsTile];
-    __shared__ long long sK[kOsTile];
     __shared__ double vbuf[kOsL];
     const int lane = threadIdx.x;
     const double dv = (mode == 1) ? *div : 1.0;
-    double s = 0.0;
-    for (int64_t base = 0; base < n_chunks; base += kOsTile) {
-        const int cnt = (int)min((int64_t)kOsTile, n_chunks - base);
-        for (int k = lane; k < cnt; k += 32) { se[k] = ce[base + k]; sK[k] = cK[base + k]; }
-        __syncwarp();
-        int c = 0;
-        while (c < cnt) {
-            int stop = c;
-            if (lane == 0) {
-                int j = c;
-                for (; j < cnt; ++j) {
-                    const int e = se[j];
-                    if (e == kOsComplex) break;
-                    const long long sb = __double_as_longlong(s);
-                    if ((int)((unsigned long long)sb >> 52) - 1023 != e) break;        // also rejects s <= 0, NaN, inf
-                    const long long M = ((sb & 0xFFFFFFFFFFFFFll) | kTwo52) + sK[j];
-                    if (M > kTwo53) break;                                             // would leave the binade inside the chunk
-                    carry_in[base + j] = s;
-                    s = os_from_int(M, e);
-                }
-                stop = j;
+    double s = 0.0;                                      // uniform across the warp
+    int64_t c = 0;
+    while (c < n_chunks) {
+        const int64_t j = c + lane;
+        const bool in = j < n_chunks;
+        const int e_j = in ? ce[j] : kOsComplex;
+        const long long K_j = in ? cK[j] : 0;
+        const long long sb = __double_as_longlong(s);
+        const int e_s = (int)((unsigned long long)sb >> 52) - 1023;      // s <= 0, NaN, inf never match a predicted binade
+        const long long m = (sb & 0xFFFFFFFFFFFFFll) | kTwo52;
+        long long inc = K_j;                                            // inclusive prefix of K over the lanes
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
+        }
+        // a chunk with K_j > 2^53 would overflow nothing here (sums of 32 x 2^61 fit) but fails the bound below
+        // carry-in still inside the binade (a chunk may END exactly on 2^(e+1); its successor then sees the new
+        // binade on the next step) and carry-out not beyond it
+        const bool ok = in && e_j != kOsComplex && e_j == e_s && (m + inc - K_j) < kTwo53 && (m + inc) <= kTwo53 && inc >= 0;
+        const unsigned bad = ~__ballot_sync(0xffffffffu, ok);
+        const int run = bad ? (__ffs(bad) - 1) : 32;                    // chunks c .. c+run-1 are committed
+        if (lane < run) carry_in[j] = os_from_int(m + inc - K_j, e_s);
+        if (run > 0) {
+            const long long tot = __shfl_sync(0xffffffffu, inc, run - 1);
+            s = os_from_int(m + tot, e_s);
+        }
+        c += run;
+        if (run < 32 && c < n_chunks) {                  // replay chunk c with the scalar chain
+            const int64_t j0 = c * kOsL;
+            const int n_el = (int)min((int64_t)kOsL, n - j0);
+#pragma unroll
+            for (int k = 0; k < kOsL / 32; ++k) {
+                const int idx = k * 32 + lane;
+                vbuf[idx] = idx < n_el ? os_term(mode, io[j0 + idx], dv, mean) : 0.0;
             }
-            stop = __shfl_sync(0xffffffffu, stop, 0);
-            c = stop;
-            if (c < cnt) {                               // replay chunk base + c with the scalar chain
-                const int64_t j0 = (base + c) * kOsL;
-                const int n_el = (int)min((int64_t)kOsL, n - j0);
+            __syncwarp();
+            if (lane == 0) {
+                carry_in[c] = s;
+                replayed[c] = 1;
+                int q = 0;
+                if (j0 == 0) { s = vbuf[0]; q = 1; }
+#pragma unroll 8
+                for (; q < n_el; ++q) {
+                    s = __dadd_rn(s, vbuf[q]);
+                    if (mode == 1) vbuf[q] = s;
+                }
+            }
+            __syncwarp();
+            if (mode == 1) {
 #pragma unroll
                 for (int k = 0; k < kOsL / 32; ++k) {
                     const int idx = k * 32 + lane;
-                    vbuf[idx] = idx < n_el ? os_term(mode, io[j0 + idx], dv, mean) : 0.0;
+                    if (idx < n_el) io[j0 + idx] = vbuf[idx];
                 }
-                __syncwarp();
-                if (lane == 0) {
-                    carry_in[base + c] = s;
-                    replayed[base + c] = 1;
-                    int j = 0;
-                    if (j0 == 0) { s = vbuf[0]; j = 1; }
-#pragma unroll 8
-                    for (; j < n_el; ++j) {
-                        s = __dadd_rn(s, vbuf[j]);
-                        if (mode == 1) vbuf[j] = s;
-                    }
-                }
-                __syncwarp();
-                if (mode == 1) {
-#pragma unroll
-                    for (int k = 0; k < kOsL / 32; ++k) {
-                        const int idx = k * 32 + lane;
-                        if (idx < n_el) io[j0 + idx] = vbuf[idx];
-                    }
-                }
-                __syncwarp();
-                ++c;
             }
+            __syncwarp();
+            s = __shfl_sync(0xffffffffu, s, 0);
+            ++c;
         }
-        __syncwarp();
     }
     if (lane == 0 && out) out[0] = s;
 }
