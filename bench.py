@@ -356,7 +356,11 @@ def run_ours(a):
 
         def e2e_step():
             vol.reset()
-            vol.integrate_batch(hd, hc, seq.fxfycxcy, seq.extrinsic)
+            if world > 1:       # frames cross PCIe once per box: 1/world per rank, all-gather over NVLink (slab.py)
+                from otslam_b200 import slab as slabmod
+                slabmod.integrate_host_sharded(vol, hd, hc, seq.fxfycxcy, seq.extrinsic, rank, world, f"cuda:{local}", stream=stream)
+            else:
+                vol.integrate_batch(hd, hc, seq.fxfycxcy, seq.extrinsic)
             return vol.stats()            # D2H read of the step's result
 
         with torch.cuda.stream(stream):
@@ -374,7 +378,9 @@ def run_ours(a):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = {"value": n * a.steps / float(t.item()), "unit": UNIT,
                "h2d_bytes_per_step": int(n * W * H * 5 + n * 16 * 8), "d2h_bytes_per_step": 16 + 16,
-               "api": "otslam_volume_reset + otslam_volume_integrate_batch(OTSLAM_MEM_HOST, pinned) + otslam_volume_stats"}
+               "api": "otslam_volume_reset + otslam_volume_integrate_batch(OTSLAM_MEM_HOST, pinned) + otslam_volume_stats" if world == 1 else
+                      "otslam_volume_reset + slab.integrate_host_sharded (H2D of 1/world of each 128-frame chunk per rank, ncclAllGather "
+                      "over NVLink, otslam_volume_integrate_batch on the resident chunk) + otslam_volume_stats"}
 
     # ---- multi-GPU: extraction + NCCL gather of the extracted points (outside the timed region)
     extra = {}

@@ -180,6 +180,23 @@ int otslam_grid_to_points(const uint8_t* gray, int width, int height, double res
 int otslam_cloud_merge_pack(int n_clouds, const double* const* points, const double* const* colors,
                             const int64_t* counts, const double* paint, uint8_t* out_records, int device);
 
+
+/* ---- the steps either side of hybrid_map.py, non-interactive */
+/* PointCloud.transform(T) (fusion/hybrid_map_manual.py:86-90, the W/S/A/D keys): p' = (T*[p,1]).xyz / w,
+ * normals rotated by T's 3x3 block; normals / out_normals nullable */
+int otslam_cloud_transform(const double* points, const double* normals, int64_t n, const double transform[16],
+                           double* out_points, double* out_normals, int device);
+/* PointCloud.get_center() (fusion/hybrid_map_manual.py:110): mean of the points, summed in index order */
+int otslam_cloud_center(const double* points, int64_t n, double center[3], int device);
+/* PointCloud.rotate(R, center) (fusion/hybrid_map_manual.py:112, the Z/C keys): p' = R*(p - center) + center */
+int otslam_cloud_rotate(const double* points, const double* normals, int64_t n, const double rotation[9],
+                        const double center[3], double* out_points, double* out_normals, int device);
+/* smart_paste(base_img, overlay_img, x, y, w, h) (fusion/2d_selective_merge.py:58-69): inside the rectangle,
+ * overlay pixels that are not within `threshold` of `unknown_pixel` replace the base map's; in place on
+ * `base`; a rectangle that leaves the image changes nothing (as in the reference) */
+int otslam_grid_smart_paste(uint8_t* base, const uint8_t* overlay, int width, int height, int x, int y, int w, int h,
+                            int unknown_pixel, int threshold, int device);
+
 #ifdef __cplusplus
 }
 #endif

@@ -216,6 +216,56 @@ __global__ void __launch_bounds__(256) sample_kernel(const double* __restrict__ 
     }
 }
 
+// ---- rigid-body edits (fusion/hybrid_map_manual.py:86-119) and the 2-D map paste (fusion/2d_selective_merge.py:58-69)
+// mode 0: p' = (T[4x4] * [p,1]).xyz / w, n' = T[0:3,0:3] * n;  mode 1: p' = R[3x3] * (p - c) + c, n' = R * n.
+// Product order ((m0*x + m1*y) + m2*z) + m3, as the oracle defines it.
+struct RigidArgs {
+    double m[16];       // mode 0: T row-major; mode 1: R in m[0..8], centre in m[9..11]
+    int mode;
+};
+__global__ void __launch_bounds__(256) rigid_kernel(const double* __restrict__ pts, const double* __restrict__ nrm, int64_t n, RigidArgs a,
+                                                    double* __restrict__ out_pts, double* __restrict__ out_nrm) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double x = pts[3 * i], y = pts[3 * i + 1], z = pts[3 * i + 2];
+    if (a.mode == 0) {
+        double h[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            h[r] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(a.m[4 * r], x), __dmul_rn(a.m[4 * r + 1], y)), __dmul_rn(a.m[4 * r + 2], z)), a.m[4 * r + 3]);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) out_pts[3 * i + r] = __ddiv_rn(h[r], h[3]);
+    } else {
+        x = __dsub_rn(x, a.m[9]); y = __dsub_rn(y, a.m[10]); z = __dsub_rn(z, a.m[11]);
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+            out_pts[3 * i + r] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(a.m[3 * r], x), __dmul_rn(a.m[3 * r + 1], y)), __dmul_rn(a.m[3 * r + 2], z)), a.m[9 + r]);
+    }
+    if (nrm && out_nrm) {
+        const double p = nrm[3 * i], q = nrm[3 * i + 1], w = nrm[3 * i + 2];
+        const int st = a.mode == 0 ? 4 : 3;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+            out_nrm[3 * i + r] = __dadd_rn(__dadd_rn(__dmul_rn(a.m[st * r], p), __dmul_rn(a.m[st * r + 1], q)), __dmul_rn(a.m[st * r + 2], w));
+    }
+}
+
+__global__ void __launch_bounds__(256) axis_extract_kernel(const double* __restrict__ pts, int64_t n, int axis, double* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = pts[3 * i + axis];
+}
+
+// one thread per pixel of the rectangle: overlay pixels that hold data (not within `threshold` of the
+// "unknown" grey) replace the base map's
+__global__ void __launch_bounds__(256) smart_paste_kernel(uint8_t* __restrict__ base, const uint8_t* __restrict__ overlay, int width, int x0,
+                                                          int y0, int w, int h, int unknown, int threshold) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= w * h) return;
+    const size_t p = (size_t)(y0 + i / w) * width + (x0 + i % w);
+    const int v = overlay[p];
+    if (v < unknown - threshold || v > unknown + threshold) base[p] = (uint8_t)v;
+}
+
 // ---- merge + paint + PLY record packing: 256 points per CTA staged through SMEM so that the
 // 27-byte records leave as coalesced 16-byte stores.
 struct MergeArgs {
@@ -464,6 +514,84 @@ int otslam_grid_to_points(const uint8_t* gray, int width, int height, double res
     OT_TRY(launch((int)((n + kItemsPerCta - 1) / kItemsPerCta), base.p, nullptr));
     timer.stop();
     OT_CUDA(cudaMemcpy(out_points, op.p, m * 24, cudaMemcpyDeviceToHost));
+    return OTSLAM_OK;
+}
+
+static int rigid_apply(const double* points, const double* normals, int64_t n, const RigidArgs& a, double* out_points, double* out_normals,
+                       int device) {
+    if (n < 0 || (n && (!points || !out_points))) return set_error(OTSLAM_ERR_INVALID, "bad arguments");
+    if (n == 0) return OTSLAM_OK;
+    OT_TRY(use_device(device));
+    DevBuf<double> dp, dn, op, on;
+    OT_CUDA(dp.alloc(n * 3)); OT_CUDA(op.alloc(n * 3));
+    OT_CUDA(cudaMemcpy(dp.p, points, n * 24, cudaMemcpyHostToDevice));
+    const bool has_n = normals && out_normals;
+    if (has_n) { OT_CUDA(dn.alloc(n * 3)); OT_CUDA(on.alloc(n * 3)); OT_CUDA(cudaMemcpy(dn.p, normals, n * 24, cudaMemcpyHostToDevice)); }
+    OpTimer timer;
+    rigid_kernel<<<(unsigned)((n + 255) / 256), 256>>>(dp.p, has_n ? dn.p : nullptr, n, a, op.p, has_n ? on.p : nullptr);
+    OT_LAUNCHED();
+    timer.stop();
+    OT_CUDA(cudaMemcpy(out_points, op.p, n * 24, cudaMemcpyDeviceToHost));
+    if (has_n) OT_CUDA(cudaMemcpy(out_normals, on.p, n * 24, cudaMemcpyDeviceToHost));
+    return OTSLAM_OK;
+}
+
+int otslam_cloud_transform(const double* points, const double* normals, int64_t n, const double transform[16], double* out_points,
+                           double* out_normals, int device) {
+    if (!transform) return set_error(OTSLAM_ERR_INVALID, "null transform");
+    RigidArgs a;
+    for (int i = 0; i < 16; ++i) a.m[i] = transform[i];
+    a.mode = 0;
+    return rigid_apply(points, normals, n, a, out_points, out_normals, device);
+}
+
+int otslam_cloud_rotate(const double* points, const double* normals, int64_t n, const double rotation[9], const double center[3],
+                        double* out_points, double* out_normals, int device) {
+    if (!rotation || !center) return set_error(OTSLAM_ERR_INVALID, "null rotation / center");
+    RigidArgs a;
+    for (int i = 0; i < 9; ++i) a.m[i] = rotation[i];
+    for (int i = 0; i < 3; ++i) a.m[9 + i] = center[i];
+    for (int i = 12; i < 16; ++i) a.m[i] = 0.0;
+    a.mode = 1;
+    return rigid_apply(points, normals, n, a, out_points, out_normals, device);
+}
+
+int otslam_cloud_center(const double* points, int64_t n, double center[3], int device) {
+    if (n < 0 || !center || (n && !points)) return set_error(OTSLAM_ERR_INVALID, "bad arguments");
+    center[0] = center[1] = center[2] = 0.0;
+    if (n == 0) return OTSLAM_OK;
+    OT_TRY(use_device(device));
+    DevBuf<double> dp, ax, tot;
+    OT_CUDA(dp.alloc(n * 3)); OT_CUDA(ax.alloc(n)); OT_CUDA(tot.alloc(3));
+    OT_CUDA(cudaMemcpy(dp.p, points, n * 24, cudaMemcpyHostToDevice));
+    OpTimer timer;
+    for (int a = 0; a < 3; ++a) {     // coordinates may be negative: the exact chain replays such chunks scalar-wise, still in index order
+        axis_extract_kernel<<<(unsigned)((n + 255) / 256), 256>>>(dp.p, n, a, ax.p);
+        OT_LAUNCHED();
+        OT_TRY(device_ordered_sum(ax.p, n, 0, nullptr, 0.0, tot.p + a, 0));
+    }
+    timer.stop();
+    double h[3];
+    OT_CUDA(cudaMemcpy(h, tot.p, 24, cudaMemcpyDeviceToHost));
+    for (int a = 0; a < 3; ++a) center[a] = h[a] / (double)n;
+    return OTSLAM_OK;
+}
+
+int otslam_grid_smart_paste(uint8_t* base, const uint8_t* overlay, int width, int height, int x, int y, int w, int h, int unknown_pixel,
+                            int threshold, int device) {
+    if (!base || !overlay || width <= 0 || height <= 0 || w < 0 || h < 0) return set_error(OTSLAM_ERR_INVALID, "bad arguments");
+    if (x < 0 || y < 0 || (int64_t)x + w > width || (int64_t)y + h > height || w == 0 || h == 0) return OTSLAM_OK;   // reference: returns the base map unchanged
+    OT_TRY(use_device(device));
+    const size_t n = (size_t)width * height;
+    DevBuf<uint8_t> db, dov;
+    OT_CUDA(db.alloc(n)); OT_CUDA(dov.alloc(n));
+    OT_CUDA(cudaMemcpy(db.p, base, n, cudaMemcpyHostToDevice));
+    OT_CUDA(cudaMemcpy(dov.p, overlay, n, cudaMemcpyHostToDevice));
+    OpTimer timer;
+    smart_paste_kernel<<<(unsigned)(((int64_t)w * h + 255) / 256), 256>>>(db.p, dov.p, width, x, y, w, h, unknown_pixel, threshold);
+    OT_LAUNCHED();
+    timer.stop();
+    OT_CUDA(cudaMemcpy(base, db.p, n, cudaMemcpyDeviceToHost));
     return OTSLAM_OK;
 }
 

@@ -328,7 +328,7 @@ struct KnnArgs {
     int k;
     int fine_rings;             // 0: no fine level
     int coarse_rings;           // ring limit on the coarse level when a top level exists (else unlimited)
-    KnnGrid fine, coarse, top;
+    KnnGrid lv[3];              // fine, coarse, top
     double* dbar;               // [n] original order
 };
 
@@ -492,17 +492,15 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_mean_dist_kernel(KnnArgs a
     double thr = 0.0;   // current k-th best (valid when found == k)
     int pos = 0;
     double reg_best = INFINITY;                    // k <= 32: the sorted k best, one per lane
+    // one copy of the search code for the three levels (three inlined copies thrashed the instruction cache:
+    // ncu showed no_instruction stalls of 2 warps per issue slot)
     bool done = false;
-    if (a.fine_rings > 0) done = knn_search_level(a.fine, a.pts, q, k, a.fine_rings, lane, best, reg_best, found, thr, pos);
-    if (!done) {
-        found = 0; thr = 0.0; pos = 0; reg_best = INFINITY;   // restart: the coarse buckets contain the fine level's finds again
+#pragma unroll 1
+    for (int level = a.fine_rings > 0 ? 0 : 1; level < 3 && !done; ++level) {
+        const int last = level == 0 ? a.fine_rings : (level == 1 ? a.coarse_rings : 0x3fffffff);
+        found = 0; thr = 0.0; pos = 0; reg_best = INFINITY;    // a coarser level's buckets contain the finer level's finds again
         __syncwarp();
-        done = knn_search_level(a.coarse, a.pts, q, k, a.coarse_rings, lane, best, reg_best, found, thr, pos);
-    }
-    if (!done) {
-        found = 0; thr = 0.0; pos = 0; reg_best = INFINITY;
-        __syncwarp();
-        knn_search_level(a.top, a.pts, q, k, 0x3fffffff, lane, best, reg_best, found, thr, pos);
+        done = knn_search_level(a.lv[level], a.pts, q, k, last, lane, best, reg_best, found, thr, pos);
     }
     if (k <= 32 && lane < found) best[lane] = reg_best;
     __syncwarp();
@@ -623,10 +621,10 @@ static int build_search(const double* d_pts, int64_t n, GridBuffers& bc, GridBuf
     const double ext[3] = {mx[0] - mn[0], mx[1] - mn[1], mx[2] - mn[2]};
     const double vol = std::max(ext[0], 1e-9) * std::max(ext[1], 1e-9) * std::max(ext[2], 1e-9);
     const double cell = std::cbrt(vol / std::max(1.0, (double)n / 2.0));
-    OT_TRY(build_grid(d_pts, n, mn, mx, cell, 1024, bc, a.coarse));
+    OT_TRY(build_grid(d_pts, n, mn, mx, cell, 1024, bc, a.lv[1]));
     a.coarse_rings = 0x3fffffff;
-    if (std::max(a.coarse.dim[0], std::max(a.coarse.dim[1], a.coarse.dim[2])) > 4 * kKnnCoarseRings) {
-        OT_TRY(build_grid(d_pts, n, mn, mx, a.coarse.cell * kKnnTopFactor, 1024, bt, a.top));
+    if (std::max(a.lv[1].dim[0], std::max(a.lv[1].dim[1], a.lv[1].dim[2])) > 4 * kKnnCoarseRings) {
+        OT_TRY(build_grid(d_pts, n, mn, mx, a.lv[1].cell * kKnnTopFactor, 1024, bt, a.lv[2]));
         a.coarse_rings = kKnnCoarseRings;
     }
     OT_TRY(upload_shell_table());
@@ -645,12 +643,12 @@ static int build_search(const double* d_pts, int64_t n, GridBuffers& bc, GridBuf
     static const int rings = getenv("OTSLAM_KNN_RINGS") ? atoi(getenv("OTSLAM_KNN_RINGS")) : kKnnFineRings;
     if (occ > 2.0 * target && rings > 0) {
         // surface-like data: points per occupied cell scale with cell^2
-        const double fine_cell = a.coarse.cell * std::sqrt(target / occ);
-        OT_TRY(build_grid(d_pts, n, mn, mx, fine_cell, 1 << 16, bf, a.fine));
+        const double fine_cell = a.lv[1].cell * std::sqrt(target / occ);
+        OT_TRY(build_grid(d_pts, n, mn, mx, fine_cell, 1 << 16, bf, a.lv[0]));
         a.fine_rings = std::min(rings, kKnnTableRings);
         if (getenv("OTSLAM_KNN_DEBUG"))
             fprintf(stderr, "knn: n %lld coarse cell %.4g (%lld cells, crowding %.1f) fine cell %.4g (%lld cells)\n", (long long)n,
-                    a.coarse.cell, (long long)bc.n_seg, occ, a.fine.cell, (long long)bf.n_seg);
+                    a.lv[1].cell, (long long)bc.n_seg, occ, a.lv[0].cell, (long long)bf.n_seg);
     }
     return OTSLAM_OK;
 }
@@ -766,7 +764,7 @@ int otslam_cloud_remove_statistical_outlier(const double* points, int64_t n, int
     OT_TRY(build_search(dp.p, n, bc, bf, bt, a));
     DevBuf<double> dbar, scal;
     OT_CUDA(dbar.alloc(n)); OT_CUDA(scal.alloc(1));
-    a.pts = dp.p; a.qpts = dp.p; a.qidx = a.fine_rings ? a.fine.idx : a.coarse.idx;   // visit queries cell by cell: neighbours share cache lines
+    a.pts = dp.p; a.qpts = dp.p; a.qidx = a.fine_rings ? a.lv[0].idx : a.lv[1].idx;   // visit queries cell by cell: neighbours share cache lines
     a.nq = n; a.mode = 0; a.n = n; a.k = k; a.dbar = dbar.p;
     knn_mean_dist_kernel<<<(unsigned)((n + kKnnWarps - 1) / kKnnWarps), kKnnWarps * 32>>>(a);
     OT_LAUNCHED();

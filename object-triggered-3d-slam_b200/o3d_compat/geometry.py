@@ -169,6 +169,64 @@ class PointCloud:
         r += other
         return r
 
+    # ---- rigid-body edits: the key callbacks of fusion/hybrid_map_manual.py:86-119 -----------------
+    def transform(self, transformation):
+        """obj_pcd.transform(T) (hybrid_map_manual.py:87), in place."""
+        T = np.ascontiguousarray(transformation, np.float64)
+        if T.shape != (4, 4):
+            raise RuntimeError("transform expects a 4x4 matrix")
+        n = len(self._points)
+        if n:
+            hn = self.has_normals()
+            op = np.empty((n, 3), np.float64)
+            on = np.empty((n, 3), np.float64) if hn else None
+            _lib.check(_lib.lib.otslam_cloud_transform(_lib.ptr(self._points), _lib.ptr(self._normals if hn else None), n, _lib.ptr(T),
+                                                       _lib.ptr(op), _lib.ptr(on), 0))
+            self._points = op
+            if hn:
+                self._normals = on
+        return self
+
+    def get_center(self):
+        """obj_pcd.get_center() (hybrid_map_manual.py:110): mean of the points (index-order sums)."""
+        c = np.zeros(3, np.float64)
+        _lib.check(_lib.lib.otslam_cloud_center(_lib.ptr(self._points), len(self._points), _lib.ptr(c), 0))
+        return c
+
+    @staticmethod
+    def get_rotation_matrix_from_xyz(rotation):
+        """R = Rx(a) @ Ry(b) @ Rz(c) (Open3D: AngleAxis(a, X) * AngleAxis(b, Y) * AngleAxis(c, Z)); the reference
+        only ever passes (0, 0, yaw) (hybrid_map_manual.py:111)."""
+        a, b, c = (float(x) for x in rotation)
+        rx = np.array([[1, 0, 0], [0, np.cos(a), -np.sin(a)], [0, np.sin(a), np.cos(a)]])
+        ry = np.array([[np.cos(b), 0, np.sin(b)], [0, 1, 0], [-np.sin(b), 0, np.cos(b)]])
+        rz = np.array([[np.cos(c), -np.sin(c), 0], [np.sin(c), np.cos(c), 0], [0, 0, 1]])
+        return rx @ ry @ rz
+
+    def rotate(self, R, center=None):
+        """obj_pcd.rotate(R, center=center) (hybrid_map_manual.py:112), in place; default centre = get_center()."""
+        R = np.ascontiguousarray(R, np.float64)
+        if R.shape != (3, 3):
+            raise RuntimeError("rotate expects a 3x3 matrix")
+        c = self.get_center() if center is None else np.ascontiguousarray(center, np.float64).reshape(3)
+        n = len(self._points)
+        if n:
+            hn = self.has_normals()
+            op = np.empty((n, 3), np.float64)
+            on = np.empty((n, 3), np.float64) if hn else None
+            _lib.check(_lib.lib.otslam_cloud_rotate(_lib.ptr(self._points), _lib.ptr(self._normals if hn else None), n, _lib.ptr(R),
+                                                    _lib.ptr(c), _lib.ptr(op), _lib.ptr(on), 0))
+            self._points = op
+            if hn:
+                self._normals = on
+        return self
+
+    def translate(self, translation, relative=True):
+        t = np.asarray(translation, np.float64).reshape(3)
+        T = np.eye(4)
+        T[:3, 3] = t if relative else t - self.get_center()
+        return self.transform(T)
+
     def select_by_index(self, indices, invert=False):
         idx = np.asarray(indices, np.int64)
         if invert:

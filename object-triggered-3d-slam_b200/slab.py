@@ -145,3 +145,68 @@ def extract_and_gather_mesh(vol, rank, world, device="cpu"):
     if rank != 0:
         return None
     return merge_mesh_parts([(g[0][r_], g[1][r_], g[2][r_], g[3][r_]) for r_ in range(world)])
+
+
+# ---------------------------------------------------------------------------------------------
+# Frame ingest for slab-sharded volumes: every rank needs every frame, but the frames only have to
+# cross PCIe ONCE per box.  Each rank uploads 1/world of a chunk from its host buffer and the ranks
+# all-gather the chunk over NVLink (ncclAllGather); uploading the whole sequence on every rank costs
+# world x the host-memory / PCIe traffic and made the 8-GPU host path slower than one GPU.
+# ---------------------------------------------------------------------------------------------
+def shard_plan(n_frames, world, chunk_frames=128):
+    """[(first frame, frames in the chunk, frames per rank)]: chunks of `chunk_frames` (rounded up to a multiple
+    of world) frames; inside a chunk rank r owns frames [first + r*per, first + (r+1)*per) -- blocked, so
+    the gathered buffer is in frame order and a short last chunk is a prefix of it."""
+    per = max(1, -(-chunk_frames // world))
+    out, c0 = [], 0
+    while c0 < n_frames:
+        n = min(per * world, n_frames - c0)
+        out.append((c0, n, per))
+        c0 += n
+    return out
+
+
+def integrate_host_sharded(vol, depth, rgb, intr, extrinsics, rank, world, device, depth_scale=1000.0, depth_trunc=3.0,
+                           chunk_frames=128, stream=None):
+    """The frame loop from HOST buffers (pinned CPU torch tensors depth [n,H,W] u16, rgb [n,H,W,3] u8, identical
+    on every rank or at least valid for this rank's shards) into a slab-sharded volume: per chunk, H2D of this
+    rank's 1/world share -> all_gather over NVLink -> integrate_batch on the resident chunk.  The upload + gather
+    of chunk k+1 is queued on a side stream before chunk k integrates.  Frame order is preserved; results are
+    identical to vol.integrate_batch(depth, rgb, ...)."""
+    n, H, W = int(depth.shape[0]), int(depth.shape[1]), int(depth.shape[2])
+    if world <= 1:
+        vol.integrate_batch(depth, rgb, intr, extrinsics, depth_scale, depth_trunc)
+        return
+    plan = shard_plan(n, world, chunk_frames)
+    per = plan[0][2]
+    side = torch.cuda.Stream(device=device)
+    main = stream if stream is not None else torch.cuda.current_stream(device)
+    bufs = [(torch.empty((per * world, H, W), dtype=depth.dtype, device=device),
+             torch.empty((per * world, H, W, 3), dtype=rgb.dtype, device=device),
+             torch.cuda.Event(), torch.cuda.Event()) for _ in range(2)]
+
+    def issue(k):
+        c0, nk, _ = plan[k]
+        gd, gc, ready, free = bufs[k & 1]
+        with torch.cuda.stream(side):
+            side.wait_event(free)                                   # the integration that last read this buffer
+            lo, hi = min(c0 + rank * per, c0 + nk), min(c0 + (rank + 1) * per, c0 + nk)
+            md, mc = gd[rank * per:(rank + 1) * per], gc[rank * per:(rank + 1) * per]
+            if hi > lo:
+                md[:hi - lo].copy_(depth[lo:hi], non_blocking=True)
+                mc[:hi - lo].copy_(rgb[lo:hi], non_blocking=True)
+            # in-place all-gather: every rank's share lands at its slot of the chunk buffer
+            dist.all_gather_into_tensor(gd.view(torch.uint8), md.view(torch.uint8))      # NCCL in torch has no 16-bit integer type
+            dist.all_gather_into_tensor(gc, mc)
+            ready.record(side)
+
+    for _, _, _, free in bufs:
+        free.record(main)
+    issue(0)
+    for k, (c0, nk, _) in enumerate(plan):
+        gd, gc, ready, free = bufs[k & 1]
+        if k + 1 < len(plan):
+            issue(k + 1)
+        main.wait_event(ready)
+        vol.integrate_batch(gd[:nk], gc[:nk], intr, extrinsics[c0:c0 + nk], depth_scale, depth_trunc)   # returns when done
+        free.record(main)

@@ -604,6 +604,41 @@ int64_t oracle_zfilter(const double* pts, const double* cols, int64_t n, double 
     return m;
 }
 
+// SURVEY 8(f) row 4 -- the rigid-body edits of fusion/hybrid_map_manual.py:86-119.
+// PointCloud.transform(T) (:87): p' = (T * [p, 1]).head<3>() / w; normals rotate with T's 3x3 block.
+// The FP64 product order is defined here as ((m0*x + m1*y) + m2*z) + m3 (Open3D leaves it to Eigen; same
+// convention as the integration's extrinsic product).
+void oracle_transform(const double* pts, const double* nrm, int64_t n, const double* T, double* out_pts, double* out_nrm) {
+    for (int64_t i = 0; i < n; ++i) {
+        const double x = pts[3 * i], y = pts[3 * i + 1], z = pts[3 * i + 2];
+        double h[4];
+        for (int r = 0; r < 4; ++r) h[r] = ((T[4 * r] * x + T[4 * r + 1] * y) + T[4 * r + 2] * z) + T[4 * r + 3];
+        for (int r = 0; r < 3; ++r) out_pts[3 * i + r] = h[r] / h[3];
+        if (nrm && out_nrm) {
+            const double a = nrm[3 * i], b = nrm[3 * i + 1], c = nrm[3 * i + 2];
+            for (int r = 0; r < 3; ++r) out_nrm[3 * i + r] = (T[4 * r] * a + T[4 * r + 1] * b) + T[4 * r + 2] * c;
+        }
+    }
+}
+// PointCloud.get_center() (:110): the mean, coordinates summed in index order.
+void oracle_center(const double* pts, int64_t n, double* c) {
+    double s[3] = {0, 0, 0};
+    for (int64_t i = 0; i < n; ++i)
+        for (int k = 0; k < 3; ++k) s[k] += pts[3 * i + k];
+    for (int k = 0; k < 3; ++k) c[k] = n > 0 ? s[k] / (double)n : 0.0;
+}
+// PointCloud.rotate(R, center) (:112): p' = R * (p - center) + center, normals' = R * n.
+void oracle_rotate(const double* pts, const double* nrm, int64_t n, const double* R, const double* c, double* out_pts, double* out_nrm) {
+    for (int64_t i = 0; i < n; ++i) {
+        const double d[3] = {pts[3 * i] - c[0], pts[3 * i + 1] - c[1], pts[3 * i + 2] - c[2]};
+        for (int r = 0; r < 3; ++r) out_pts[3 * i + r] = ((R[3 * r] * d[0] + R[3 * r + 1] * d[1]) + R[3 * r + 2] * d[2]) + c[r];
+        if (nrm && out_nrm) {
+            const double a = nrm[3 * i], b = nrm[3 * i + 1], cc = nrm[3 * i + 2];
+            for (int r = 0; r < 3; ++r) out_nrm[3 * i + r] = (R[3 * r] * a + R[3 * r + 1] * b) + R[3 * r + 2] * cc;
+        }
+    }
+}
+
 // PointCloud.create_from_rgbd_image (check_one_frame.py:27): dense FP64
 // back-projection in row-major pixel order, colour/255.
 int64_t oracle_backproject_rgbd(const float* depth, const uint8_t* rgb, int W, int H, double fx, double fy, double cx,

@@ -247,3 +247,41 @@ def pack_ply_cloud(pts, cols):
     out = np.empty((len(p), 27), np.uint8)
     lib().oracle_pack_ply_cloud(_p(p), _p(c), C.c_int64(len(p)), _p(out))
     return out
+
+
+def transform(pts, nrm, T):
+    p = np.ascontiguousarray(pts, np.float64)
+    q = None if nrm is None else np.ascontiguousarray(nrm, np.float64)
+    op, on = np.empty_like(p), None if q is None else np.empty_like(q)
+    lib().oracle_transform(_p(p), _p(q), C.c_int64(len(p)), _p(np.ascontiguousarray(T, np.float64).reshape(16)), _p(op), _p(on))
+    return op, on
+
+
+def center(pts):
+    p = np.ascontiguousarray(pts, np.float64)
+    c = np.zeros(3)
+    lib().oracle_center(_p(p), C.c_int64(len(p)), _p(c))
+    return c
+
+
+def rotate(pts, nrm, R, c):
+    p = np.ascontiguousarray(pts, np.float64)
+    q = None if nrm is None else np.ascontiguousarray(nrm, np.float64)
+    op, on = np.empty_like(p), None if q is None else np.empty_like(q)
+    lib().oracle_rotate(_p(p), _p(q), C.c_int64(len(p)), _p(np.ascontiguousarray(R, np.float64).reshape(9)),
+                        _p(np.ascontiguousarray(c, np.float64)), _p(op), _p(on))
+    return op, on
+
+
+def smart_paste(base_img, overlay_img, x, y, w, h):
+    """/root/reference/fusion/2d_selective_merge.py:58-69, restated (NumPy, in place on a copy)."""
+    base_img = base_img.copy()
+    h_img, w_img = base_img.shape
+    if x < 0 or y < 0 or x + w > w_img or y + h > h_img:
+        return base_img
+    roi_base = base_img[y:y + h, x:x + w]
+    roi_new = overlay_img[y:y + h, x:x + w]
+    unknown_pixel, threshold = 205, 5
+    has_data_mask = (roi_new < (unknown_pixel - threshold)) | (roi_new > (unknown_pixel + threshold))
+    roi_base[has_data_mask] = roi_new[has_data_mask]
+    return base_img

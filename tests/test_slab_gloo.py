@@ -99,3 +99,17 @@ def test_merge_mesh_parts_unifies_duplicates():
     tri = verts[faces]
     assert {tuple(map(tuple, t)) for t in tri.tolist()} == {tuple(map(tuple, v[[0, 1, 2]].tolist())), tuple(map(tuple, v1[[0, 2, 1]].tolist()))}
     assert slab.slab_spec(0, 1) is None and slab.slab_spec(3, 8) == (0, 8, 8, 3)
+
+
+def test_shard_plan_covers_every_frame_once_in_order():
+    """Host ingest for slab volumes (slab.integrate_host_sharded): chunks are split into per-rank blocks whose
+    concatenation in rank order is the chunk in frame order."""
+    from otslam_b200 import slab
+    for n, world, chunk in ((1000, 8, 256), (200, 8, 256), (7, 2, 256), (33, 4, 32), (1, 8, 256), (513, 3, 100)):
+        seen = []
+        for c0, nk, per in slab.shard_plan(n, world, chunk):
+            assert nk <= per * world and per * world >= min(chunk, 1)
+            for r in range(world):
+                lo, hi = min(c0 + r * per, c0 + nk), min(c0 + (r + 1) * per, c0 + nk)
+                seen += list(range(lo, hi))
+        assert seen == list(range(n))
