@@ -21,8 +21,8 @@ def read_image(filename):
     if a is None:
         print(f"[Open3D WARNING] Read image failed: unable to open file: {filename}")
         return geometry.Image()
-    if a.ndim == 3:
-        a = a[..., :3][..., ::-1]
+    if a.ndim == 3:             # OpenCV decodes to BGR(A); Open3D hands out RGB.  cvtColor is ~10x a strided NumPy copy
+        a = cv2.cvtColor(a, cv2.COLOR_BGRA2RGB if a.shape[2] == 4 else cv2.COLOR_BGR2RGB) if a.shape[2] in (3, 4) else a[..., :3][..., ::-1]
     return geometry.Image(np.ascontiguousarray(a))
 
 

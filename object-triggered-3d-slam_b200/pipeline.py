@@ -7,6 +7,7 @@ Here the files are decoded on the host in chunks and each chunk goes to the GPU 
 per-frame failures keep the reference's semantics: abort (reconstruct_rgbd.py, no try) or
 print-and-skip (reconstruct_rgbd_filter.py:108-109, multi_reconstruct_rgbd_filter.py:102-103).
 """
+import os
 import sys
 
 import numpy as np
@@ -33,28 +34,60 @@ def load_frame(color_path, depth_path, pose_path, intrinsics, T_fix):
     return color, depth, extrinsic
 
 
+def _decode_workers():
+    return max(1, min(16, int(os.environ.get("OTSLAM_DECODE_THREADS", "0")) or (os.cpu_count() or 1)))
+
+
+def _try_load(triple, intrinsics, T_fix):
+    cp, dp, pp, _ = triple
+    try:
+        return load_frame(cp, dp, pp, intrinsics, T_fix), None
+    except Exception as err:  # noqa: BLE001
+        return None, err
+
+
 def integrate_files(volume, triples, intrinsics, T_fix, depth_scale=1000.0, depth_trunc=3.0, skip_errors=False,
                     progress=None, on_error=None):
-    """Integrate capture triples [(color, depth, pose, label)] in order. Returns frames integrated."""
+    """Integrate capture triples [(color, depth, pose, label)] in order. Returns frames integrated.
+
+    JPEG / PNG decoding is what bounds this loop once integration runs on the GPU (~5 ms per frame pair on
+    one core against ~0.02 ms of GPU work), so the files of a chunk are decoded by a thread pool (OpenCV
+    releases the GIL) and chunk k+1 is decoded while the GPU integrates chunk k (the C-ABI call releases the
+    GIL as well).  Results are consumed in file order, so the per-frame semantics -- abort on the first bad
+    frame, or print-and-skip -- and the frame order seen by the volume are exactly the sequential loop's."""
+    from concurrent.futures import ThreadPoolExecutor
     done = 0
     n = len(triples)
-    for c0 in range(0, n, CHUNK_FRAMES):
-        cols, deps, exts = [], [], []
-        for k, (cp, dp, pp, label) in enumerate(triples[c0:c0 + CHUNK_FRAMES]):
-            try:
-                c, d, e = load_frame(cp, dp, pp, intrinsics, T_fix)
-            except Exception as err:  # noqa: BLE001
-                if not skip_errors:
-                    raise
-                if on_error:
-                    on_error(label, err)
-                continue
-            cols.append(c); deps.append(d); exts.append(e)
-            if progress:
-                progress(label, c0 + k + 1, n)
-        if exts:
-            volume.integrate_sequence(np.stack(deps), np.stack(cols), intrinsics, np.stack(exts), depth_scale, depth_trunc)
-            done += len(exts)
+    chunks = [triples[c0:c0 + CHUNK_FRAMES] for c0 in range(0, n, CHUNK_FRAMES)]
+    if not chunks:
+        return 0
+    with ThreadPoolExecutor(max_workers=_decode_workers()) as pool:
+        def submit(chunk):
+            return [pool.submit(_try_load, t, intrinsics, T_fix) for t in chunk]
+
+        pending = submit(chunks[0])
+        for ci, chunk in enumerate(chunks):
+            futures = pending
+            cols, deps, exts = [], [], []
+            for k, (fut, triple) in enumerate(zip(futures, chunk)):
+                frame, err = fut.result()
+                label = triple[3]
+                if err is not None:
+                    if not skip_errors:
+                        for f in futures[k + 1:]:
+                            f.cancel()
+                        raise err
+                    if on_error:
+                        on_error(label, err)
+                    continue
+                c, d, e = frame
+                cols.append(c); deps.append(d); exts.append(e)
+                if progress:
+                    progress(label, ci * CHUNK_FRAMES + k + 1, n)
+            pending = submit(chunks[ci + 1]) if ci + 1 < len(chunks) else []     # decoded while this chunk integrates
+            if exts:
+                volume.integrate_sequence(np.stack(deps), np.stack(cols), intrinsics, np.stack(exts), depth_scale, depth_trunc)
+                done += len(exts)
     return done
 
 

@@ -149,6 +149,41 @@ def test_load_frame_errors_follow_reference_semantics(tmp_path):
         pipeline.integrate_files(FakeVolume(), triples, intr, synth.T_FIX, skip_errors=False)
 
 
+def test_integrate_files_threaded_decode_keeps_file_order(tmp_path, monkeypatch):
+    """Chunks are decoded by a thread pool one chunk ahead of the integration; the volume must still see
+    every frame exactly once, in file order, with skipped frames dropped in place."""
+    intr = o3d.camera.PinholeCameraIntrinsic(64, 48, 56.0, 56.0, 32.5, 24.5)
+    seq = synth.make_sequence("table", 11, intr=(64, 48, 56.0, 56.0, 32.5, 24.5))
+    base = str(tmp_path / "scan")
+    synth.write_capture_tree(seq, base)
+    monkeypatch.setattr(pipeline, "CHUNK_FRAMES", 4)
+    monkeypatch.setenv("OTSLAM_DECODE_THREADS", "3")
+
+    def triple(i, depth_ok=True):
+        return (os.path.join(base, "color", f"Object_0_{i}.jpg"),
+                os.path.join(base, "depth", f"Object_0_{i}.png" if depth_ok else "missing.png"),
+                os.path.join(base, "poses", f"Object_0_{i}.txt"), i)
+
+    triples = [triple(i, depth_ok=(i not in (3, 8))) for i in range(1, 12)]
+
+    class Recorder:
+        def __init__(self):
+            self.ext, self.calls = [], []
+
+        def integrate_sequence(self, d, c, intr_, e, s, t):
+            assert d.shape[0] == c.shape[0] == e.shape[0]
+            self.calls.append(len(e))
+            self.ext += [x for x in e]
+
+    rec, errs, prog = Recorder(), [], []
+    n = pipeline.integrate_files(rec, triples, intr, synth.T_FIX, skip_errors=True, on_error=lambda l, e: errs.append(l),
+                                 progress=lambda label, i, total: prog.append((label, i, total)))
+    assert n == 9 and errs == [3, 8] and rec.calls == [3, 3, 3]
+    want = [np.linalg.inv(np.loadtxt(triple(i)[2]) @ synth.T_FIX) for i in range(1, 12) if i not in (3, 8)]
+    assert all((a == b).all() for a, b in zip(rec.ext, want))
+    assert [p[0] for p in prog] == [i for i in range(1, 12) if i not in (3, 8)] and prog[-1][1:] == (11, 11)
+
+
 def test_synth_matches_capture_contract():
     seq = synth.make_sequence("table", 300, subsample=(0, 150))
     d, c = seq.numpy()
