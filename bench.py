@@ -52,7 +52,7 @@ def parse():
     ap.add_argument("--slab-halo", type=int, default=0, help="multi-GPU: 1 = replicate +1 halo blocks, 0 = exchange planes")
     ap.add_argument("--emulate-world", type=int, default=0, help="dev: single GPU integrating only rank 0's slabs of an N-rank run")
     ap.add_argument("--emulate-rank", type=int, default=0, help="dev: which rank's slabs --emulate-world integrates")
-    ap.add_argument("--slab-axis", type=int, default=0, help="multi-GPU: 0/1/2 = x/y/z slabs, 3 = diagonal (x+y+z) slabs")
+    ap.add_argument("--slab-axis", type=int, default=3, help="multi-GPU: 0/1/2 = x/y/z slabs, 3 = diagonal slabs (ownership by kx + ky; halo 0 only)")
     ap.add_argument("--zsplit", type=int, default=0, help="dev: CTAs per block along z in the integration kernel")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -414,7 +414,7 @@ def run_ours(a):
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": workload_name(a), "frames_per_step": n, "frames_per_launch": a.batch,
                            "parallelism": "single GPU" if world == 1 else (
-                               f"x-axis slabs of {a.slab_thickness} block(s), cyclic over {world} ranks, " +
+                               f"{['x-axis', 'y-axis', 'z-axis', 'diagonal (kx+ky)'][a.slab_axis]} slabs of {a.slab_thickness} block(s), cyclic over {world} ranks, " +
                                ("+1 block halo integrated redundantly" if a.slab_halo else
                                 "owned blocks only; boundary planes exchanged once before extraction")),
                            "l2": "inputs (%.0f MB) + volume (%.0f MB) exceed the 126 MB L2; no flush needed" % (
@@ -430,6 +430,8 @@ def run_ours(a):
 
 def main():
     a = parse()
+    if a.slab_halo and a.slab_axis == 3:
+        a.slab_axis = 0             # the replicated-halo mode exists for axis slabs only
     if a.hd and a.voxel == 0.005:
         a.voxel = 0.002
     if a.impl == "reference":

@@ -34,12 +34,12 @@ extern "C" {
 
 typedef struct otslam_volume otslam_volume;
 
-/* Spatial slab sharding of the block grid across the GPUs of one box: block key k on
- * `axis` is owned by rank (floor(k / thickness) mod n_ranks).  Extraction needs the +1 neighbour
- * voxels of owned blocks: halo = 1 integrates the +1 neighbour blocks redundantly on this rank (no
- * exchange at all); halo = 0 integrates owned blocks only and the ranks exchange the 256-voxel
- * boundary planes once before extraction (otslam_volume_halo_export / _import).
- * n_ranks == 1: keep everything. */
+/* Spatial slab sharding of the block grid across the GPUs of one box: a block is owned by rank
+ * (floor(c / thickness) mod n_ranks), where c is its key on `axis` (0 / 1 / 2) or kx + ky for axis = 3
+ * ("diagonal" slabs: axis-aligned walls and floors spread over all ranks; needs halo = 0).  Extraction needs
+ * the +1 neighbour voxels of owned blocks: halo = 1 integrates the +1 neighbour blocks redundantly on this rank
+ * (no exchange at all); halo = 0 integrates owned blocks only and the ranks exchange boundary pieces once
+ * before extraction (otslam_volume_halo_export / _import).  n_ranks == 1: keep everything. */
 typedef struct {
     int32_t axis, thickness, n_ranks, rank, halo;
 } otslam_slab_spec;
@@ -114,11 +114,13 @@ int otslam_volume_export_blocks(otslam_volume* v, int32_t* keys, float* tsdf, fl
 /* sum of all voxel weights (== number of voxel updates since reset) and voxels with weight > 0 */
 int otslam_volume_stats(otslam_volume* v, int64_t* n_blocks, uint64_t* weight_sum, uint64_t* n_observed);
 
-/* ---- halo exchange for slab.halo == 0 (the path's only inter-GPU exchange besides the final
- *      gather): export the low-side boundary plane (coordinate 0 on the slab axis; 256 voxel
- *      records of 16 bytes, opaque) of every owned block whose -axis neighbour block belongs to
- *      another rank, with that rank as destination; import inserts received planes as non-owned
- *      blocks.  Call export with NULL buffers to get the count. */
+/* ---- halo exchange for slab.halo == 0 (the path's only inter-GPU exchange of voxel data besides the final
+ *      gather): export the low-side boundary pieces (256 voxel records of 16 bytes each, opaque) of every
+ *      owned block whose -axis neighbour block belongs to another rank, with that rank as destination.
+ *      keys [n][4] = block key + piece kind: 0 / 1 / 2 = the plane x / y / z = 0, 3 = the column x = y = 0.
+ *      Axis slabs send one plane per boundary block; diagonal slabs send the x and the y plane to the owner
+ *      of the -x / -y neighbours and the column to the owner of the -x-y neighbour.  import inserts received
+ *      pieces into (non-owned) blocks.  Call export with NULL buffers to get the count. */
 int otslam_volume_halo_export(otslam_volume* v, int64_t* n, int32_t* keys, int32_t* dest_rank, void* planes);
 int otslam_volume_halo_import(otslam_volume* v, int64_t n, const int32_t* keys, const void* planes);
 

@@ -126,19 +126,23 @@ __host__ __device__ inline int slab_owner(const SlabSpec& s, int k) {
     int m = floordiv_i(k, s.thickness) % s.n_ranks;
     return m < 0 ? m + s.n_ranks : m;
 }
+// the coordinate that decides ownership: one block axis (0/1/2), or kx + ky for axis 3 ("diagonal" slabs:
+// any axis-aligned wall or floor then spreads over all ranks, which single-axis slabs cannot do for planes
+// perpendicular to their axis)
+__host__ __device__ inline int slab_coord(const SlabSpec& s, int kx, int ky, int kz) {
+    return s.axis == 0 ? kx : (s.axis == 1 ? ky : (s.axis == 2 ? kz : kx + ky));
+}
 __host__ __device__ inline bool slab_owns(const SlabSpec& s, int kx, int ky, int kz) {
     if (s.n_ranks <= 1) return true;
-    int a = s.axis == 0 ? kx : (s.axis == 1 ? ky : kz);
-    return slab_owner(s, a) == s.rank;
+    return slab_owner(s, slab_coord(s, kx, ky, kz)) == s.rank;
 }
-// the same on the slab-axis coordinate alone
+// the same on the ownership coordinate alone
 __host__ __device__ inline bool slab_keeps_coord(const SlabSpec& s, int a) {
     return slab_owner(s, a) == s.rank || (s.halo && slab_owner(s, a - 1) == s.rank);
 }
 __host__ __device__ inline bool slab_keeps(const SlabSpec& s, int kx, int ky, int kz) {
     if (s.n_ranks <= 1) return true;
-    int a = s.axis == 0 ? kx : (s.axis == 1 ? ky : kz);
-    return slab_owner(s, a) == s.rank || (s.halo && slab_owner(s, a - 1) == s.rank);
+    return slab_keeps_coord(s, slab_coord(s, kx, ky, kz));
 }
 
 // Scratch cache for the operators' temporaries and results: cudaMalloc / cudaFree cost 0.1-0.5 ms each

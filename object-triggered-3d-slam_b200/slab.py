@@ -53,7 +53,7 @@ def exchange_halo(vol, rank, world, device="cpu"):
             ops += [dist.P2POp(dist.isend, tk, r), dist.P2POp(dist.isend, tp, r)]
         n_in = allc[r][rank]
         if n_in:
-            rk = torch.empty((n_in, 3), dtype=torch.int32, device=device)
+            rk = torch.empty((n_in, 4), dtype=torch.int32, device=device)
             rp = torch.empty((n_in, rec), dtype=torch.uint8, device=device)
             recv.append((rk, rp))
             ops += [dist.P2POp(dist.irecv, rk, r), dist.P2POp(dist.irecv, rp, r)]

@@ -158,10 +158,10 @@ class TSDFVolume:
         return {"n_blocks": nb.value, "weight_sum": ws.value, "n_observed": no.value}
 
     def halo_export(self):
-        """(keys [n,3] i32, dest rank [n] i32, planes [n,4096] u8) for the slab halo exchange."""
+        """(keys [n,4] i32 = block key + piece kind, dest rank [n] i32, pieces [n,4096] u8) for the slab halo exchange."""
         n = C.c_int64(0)
         _lib.check(_lib.lib.otslam_volume_halo_export(self._h, C.byref(n), None, None, None))
-        keys = np.empty((n.value, 3), np.int32)
+        keys = np.empty((n.value, 4), np.int32)
         dest = np.empty(n.value, np.int32)
         planes = np.empty((n.value, 4096), np.uint8)
         if n.value:

@@ -82,7 +82,8 @@ inline int slab_owner(const Volume* v, int k) {
     int m = floordiv(k, v->slab_thickness) % v->slab_ranks;
     return m < 0 ? m + v->slab_ranks : m;
 }
-inline int key_axis(const Key& k, int axis) { return axis == 0 ? k.x : (axis == 1 ? k.y : k.z); }
+// ownership coordinate: a block axis, or kx + ky for axis 3 (diagonal slabs)
+inline int key_axis(const Key& k, int axis) { return axis == 0 ? k.x : (axis == 1 ? k.y : (axis == 2 ? k.z : k.x + k.y)); }
 // a rank keeps the blocks it owns plus a one-block halo on the +axis side (the +1 neighbours of
 // owned blocks), so extraction never needs another rank's voxels.
 inline bool slab_keeps(const Volume* v, const Key& k) {
@@ -282,49 +283,68 @@ void* oracle_volume_create(double voxel_length, double sdf_trunc) {
 }
 int oracle_volume_set_slab(void* h, int axis, int thickness, int n_ranks, int rank, int halo) {
     Volume* v = (Volume*)h;
-    if (axis < 0 || axis > 2 || thickness < 1 || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail("bad slab spec");
+    if (axis < 0 || axis > 3 || thickness < 1 || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail("bad slab spec");
+    if (axis == 3 && halo && n_ranks > 1) return fail("diagonal slabs need halo = 0");
     v->slab_axis = axis; v->slab_thickness = thickness; v->slab_ranks = n_ranks; v->slab_rank = rank; v->slab_halo = halo ? 1 : 0;
     return 0;
 }
 
-// Halo exchange for slab_halo == 0: the low-side boundary plane (coordinate 0 on the slab
-// axis, 256 voxels) of every owned block whose -axis neighbour belongs to another rank.  Plane
-// voxel (u, v) = the two other axes in increasing order; per voxel tsdf, weight, colour[3].
+// Halo exchange for slab_halo == 0: the low-side boundary pieces (256 voxels each) of every owned
+// block whose -axis neighbour belongs to another rank.  keys [n][4] = block key + piece kind: 0 / 1 / 2 = the
+// plane x / y / z = 0 with voxel (u, w) = the two other axes in increasing order, 3 = the column x = y = 0
+// (w = z; entries with u > 0 are zero).  Axis slabs send one plane; diagonal slabs (axis 3, coordinate
+// kx + ky) send the x and y planes to the owner of coordinate a - 1 and the column to the owner of a - 2.
+static void piece_coords(int kind, int u, int w, int c[3]) {
+    if (kind == 3) { c[0] = 0; c[1] = 0; c[2] = w; return; }
+    c[kind] = 0; c[(kind == 0) ? 1 : 0] = u; c[(kind == 2) ? 1 : 2] = w;
+}
 int64_t oracle_volume_halo_export(void* h, int32_t* keys, int32_t* dest, float* tsdf, float* weight, double* color) {
     Volume* v = (Volume*)h;
     int64_t n = 0;
     if (v->slab_ranks <= 1) return 0;
-    for (Block* b : sorted_blocks(v)) {
-        if (!slab_owns(v, b->key)) continue;
-        const int d = slab_owner(v, key_axis(b->key, v->slab_axis) - 1);
-        if (d == v->slab_rank) continue;
+    auto emit = [&](Block* b, int kind, int d) {
         if (keys) {
-            keys[3 * n] = b->key.x; keys[3 * n + 1] = b->key.y; keys[3 * n + 2] = b->key.z;
+            keys[4 * n] = b->key.x; keys[4 * n + 1] = b->key.y; keys[4 * n + 2] = b->key.z; keys[4 * n + 3] = kind;
             dest[n] = d;
             for (int u = 0; u < RES; ++u)
                 for (int w = 0; w < RES; ++w) {
+                    const int64_t o = n * 256 + u * 16 + w;
+                    if (kind == 3 && u > 0) { tsdf[o] = 0.f; weight[o] = 0.f; color[3 * o] = color[3 * o + 1] = color[3 * o + 2] = 0.0; continue; }
                     int c[3];
-                    c[v->slab_axis] = 0; c[(v->slab_axis == 0) ? 1 : 0] = u; c[(v->slab_axis == 2) ? 1 : 2] = w;
-                    const int idx = c[0] * 256 + c[1] * 16 + c[2], o = (int)(n * 256 + u * 16 + w);
+                    piece_coords(kind, u, w, c);
+                    const int idx = c[0] * 256 + c[1] * 16 + c[2];
                     tsdf[o] = b->tsdf[idx]; weight[o] = b->weight[idx];
                     for (int k = 0; k < 3; ++k) color[3 * o + k] = b->color[3 * idx + k];
                 }
         }
         ++n;
+    };
+    for (Block* b : sorted_blocks(v)) {
+        if (!slab_owns(v, b->key)) continue;
+        const int a = key_axis(b->key, v->slab_axis);
+        const int d1 = slab_owner(v, a - 1);
+        if (v->slab_axis < 3) {
+            if (d1 != v->slab_rank) emit(b, v->slab_axis, d1);
+        } else {
+            if (d1 != v->slab_rank) { emit(b, 0, d1); emit(b, 1, d1); }
+            const int d2 = slab_owner(v, a - 2);
+            if (d2 != v->slab_rank && d2 != d1) emit(b, 3, d2);
+        }
     }
     return n;
 }
 int oracle_volume_halo_import(void* h, int64_t n, const int32_t* keys, const float* tsdf, const float* weight, const double* color) {
     Volume* v = (Volume*)h;
     for (int64_t i = 0; i < n; ++i) {
-        Key k{keys[3 * i], keys[3 * i + 1], keys[3 * i + 2]};
+        Key k{keys[4 * i], keys[4 * i + 1], keys[4 * i + 2]};
+        const int kind = keys[4 * i + 3];
         auto it = v->blocks.find(k);
         if (it == v->blocks.end()) it = v->blocks.emplace(k, new Block(k)).first;
         Block* b = it->second;
-        for (int u = 0; u < RES; ++u)
+        for (int u = 0; u < (kind == 3 ? 1 : RES); ++u)
             for (int w = 0; w < RES; ++w) {
                 int c[3];
-                c[v->slab_axis] = 0; c[(v->slab_axis == 0) ? 1 : 0] = u; c[(v->slab_axis == 2) ? 1 : 2] = w;
+                piece_coords(kind, u, w, c);
                 const int idx = c[0] * 256 + c[1] * 16 + c[2];
                 const int64_t o = i * 256 + u * 16 + w;
                 b->tsdf[idx] = tsdf[o]; b->weight[idx] = weight[o];

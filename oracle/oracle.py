@@ -118,9 +118,9 @@ class Volume:
         return keys, tsdf, weight, col
 
     def halo_export(self):
-        """(keys [n,3] i32, dest rank [n] i32, planes): boundary planes for the halo exchange."""
+        """(keys [n,4] i32 = block key + piece kind, dest rank [n] i32, pieces): boundary pieces for the halo exchange."""
         n = int(lib().oracle_volume_halo_export(self.h, None, None, None, None, None))
-        keys = np.empty((n, 3), np.int32); dest = np.empty(n, np.int32)
+        keys = np.empty((n, 4), np.int32); dest = np.empty(n, np.int32)
         tsdf = np.empty((n, 256), np.float32); w = np.empty((n, 256), np.float32); col = np.empty((n, 256, 3), np.float64)
         lib().oracle_volume_halo_export(self.h, _p(keys), _p(dest), _p(tsdf), _p(w), _p(col))
         # one opaque byte record per block so the exchange code is layout agnostic

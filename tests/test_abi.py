@@ -60,8 +60,11 @@ def test_argument_validation_before_cuda():
     assert _lib.lib.otslam_volume_create(-1.0, 0.04, 1, 0, None, C.byref(h)) == _lib.ERR_INVALID
     assert "voxel_length" in _lib.last_error()
     assert _lib.lib.otslam_volume_create(0.01, 0.04, 7, 0, None, C.byref(h)) == _lib.ERR_INVALID
-    bad = _lib.SlabSpec(3, 8, 2, 0)
+    bad = _lib.SlabSpec(4, 8, 2, 0)
     assert _lib.lib.otslam_volume_create(0.01, 0.04, 1, 0, C.byref(bad), C.byref(h)) == _lib.ERR_INVALID
+    diag_with_halo = _lib.SlabSpec(3, 1, 2, 0, 1)                 # diagonal slabs need the exchange mode
+    assert _lib.lib.otslam_volume_create(0.01, 0.04, 1, 0, C.byref(diag_with_halo), C.byref(h)) == _lib.ERR_INVALID
+    assert "halo = 0" in _lib.last_error()
     assert _lib.lib.otslam_volume_reset(None) == _lib.ERR_INVALID
     n = C.c_int64(0)
     assert _lib.lib.otslam_cloud_voxel_down_sample(None, None, 0, -1.0, None, None, None, None, C.byref(n), 0) == _lib.ERR_INVALID
