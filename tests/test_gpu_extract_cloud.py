@@ -226,3 +226,19 @@ def test_grid_points_and_merge_pack(tmp_path):
     back = o3d.io.read_point_cloud(p)
     assert (back.points == pc.points).all() and np.abs(back.colors - pc.colors).max() <= 0.5 / 255 + 1e-12
     assert len(open(p, "rb").read().split(b"end_header\n", 1)[1]) == 27 * 1000
+
+
+def test_scratch_cache_and_operator_timer():
+    """Operators reuse cached device blocks (csrc/scratch.cu) and report the device time of their kernel section."""
+    import otslam_b200.o3d_compat as o3d
+    from otslam_b200 import _lib
+    rng = np.random.default_rng(5)
+    pc = o3d.geometry.PointCloud()
+    pc.points = rng.random((50000, 3))
+    a = pc.voxel_down_sample(0.05)
+    assert 0.0 < _lib.last_op_device_ms() < 1000.0
+    assert _lib.lib.otslam_trim_scratch() == 0                 # cache back to the driver ...
+    b = pc.voxel_down_sample(0.05)                             # ... and the operators still work, same result
+    assert (np.asarray(a.points) == np.asarray(b.points)).all()
+    want, _, _, _ = oracle.voxel_down_sample(np.asarray(pc.points), None, 0.05)
+    assert (np.asarray(b.points) == want).all()
