@@ -220,6 +220,44 @@ def post_stage(a, vol, n_blocks, peak):
     return out
 
 
+def hybrid_merge_stage(peak, n_obj=20, per_obj=1_000_000, map_px=2000):
+    """BASELINE.json configs[4]: fusion/hybrid_map.py -- 2-D occupancy grid -> Z = 0 points (reference :45-55, a Python
+    per-pixel loop) and the paint + concatenate + PLY-record packing of `n_obj` object clouds of `per_obj` points
+    (reference :59,88-91,115,121), through the C ABI with host buffers.  Algorithmic bytes per SURVEY 8(d):
+    1 B x w*h + 24 B x sum(N_obj) read, 27 B x (P + sum(N_obj)) written."""
+    import ctypes as C
+    import numpy as np
+    import otslam_b200.o3d_compat as o3d
+    from otslam_b200 import _lib, synth
+    out = {}
+    img = synth.occupancy_map(map_px, map_px, 0.02, 0)
+    mp = np.empty((img.size, 3))
+    nmap = C.c_int64(0)
+
+    def grid():
+        _lib.check(_lib.lib.otslam_grid_to_points(_lib.ptr(img), img.shape[1], img.shape[0], 0.05, -50.0, -50.0, 100, _lib.ptr(mp),
+                                                  C.byref(nmap), 0))
+    grid()
+    t0 = time.perf_counter()
+    grid()
+    out["grid_to_points"] = {"wall_ms": 1e3 * (time.perf_counter() - t0), "device_ms": _lib.last_op_device_ms(), "pixels": int(img.size),
+                             "points": int(nmap.value)}
+    rng = np.random.default_rng(0)
+    objs = [rng.random((per_obj, 3)) for _ in range(n_obj)]
+    clouds = [mp[:nmap.value]] + objs
+    paint = [[0.2, 0.2, 0.2]] + [[1.0, 0.0, 0.0]] * n_obj
+    o3d.io.pack_cloud_records(clouds, paint=paint)
+    t0 = time.perf_counter()
+    rec = o3d.io.pack_cloud_records(clouds, paint=paint)
+    wall, dev = time.perf_counter() - t0, _lib.last_op_device_ms()
+    b = img.size + 24.0 * n_obj * per_obj + 27.0 * len(rec)
+    out["merge_paint_pack"] = {"wall_ms": 1e3 * wall, "device_ms": dev, "points": int(len(rec)), "algorithmic_MB": b / 1e6,
+                               "device_GBps": b / (dev * 1e-3) / 1e9 if dev > 0 else None,
+                               "frac_of_hbm_peak": b / (dev * 1e-3) / 1e9 / peak if dev > 0 else None,
+                               "note": "wall = pageable H2D of 480 MB + kernel + D2H of 540 MB (PCIe-bound); device = the kernel"}
+    return out
+
+
 def files_e2e(a, seq, n_files=128):
     """The drop-in script's loop as a user runs it: a capture tree on disk (color/*.jpg, depth/*.png, poses/*.txt as
     scanner_node.cpp writes them) -> pipeline.integrate_files (thread-pool decode one chunk ahead of the GPU) into
@@ -448,6 +486,10 @@ def run_ours(a):
             vol.reset()
             vol.integrate_batch(depth_dev, rgb_dev, seq.fxfycxcy, seq.extrinsic)
             post = post_stage(a, vol, stats["n_blocks"], peak)
+            try:
+                post["hybrid_map_config5"] = hybrid_merge_stage(peak)
+            except Exception as e:  # noqa: BLE001
+                post["hybrid_map_config5"] = {"error": repr(e)}
             try:
                 post["files_e2e"] = files_e2e(a, seq)
             except Exception as e:  # noqa: BLE001 -- informational; never let it take the bench line down
