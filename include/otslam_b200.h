@@ -55,6 +55,10 @@ double otslam_last_op_device_ms(void);
 /* operators keep their device temporaries in a per-device cache (cudaMalloc / cudaFree cost more
  * than their kernels); this returns the cached blocks to the driver */
 int otslam_trim_scratch(void);
+/* page-locked host staging memory for the frame loop's inputs (otslam_volume_integrate_batch copies from pinned
+ * memory at PCIe speed and truly asynchronously; from pageable memory the driver stages through its own buffer) */
+int otslam_host_alloc(uint64_t bytes, void** out);
+int otslam_host_free(void* p);
 
 /* device self-test of the integration kernel's shared-reciprocal division and ALU floor against
  * the IEEE intrinsics (__fdiv_rn, F2I) on n pseudo-random operand triples; *mismatches must be 0. */

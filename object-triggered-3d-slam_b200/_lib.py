@@ -35,6 +35,8 @@ _SIGS = {
     "otslam_launch_count": (_i64, []),
     "otslam_last_op_device_ms": (_d, []),
     "otslam_trim_scratch": (_i, []),
+    "otslam_host_alloc": (_i, [_u64, C.POINTER(_vp)]),
+    "otslam_host_free": (_i, [_vp]),
     "otslam_selftest_division": (_i, [_u64, _u64, C.POINTER(_u64), _i]),
     "otslam_selftest_ordered_sum": (_i, [_i64, _u64, _i, C.POINTER(_u64), _i]),
     "otslam_volume_create": (_i, [_d, _d, _i, _i, C.POINTER(SlabSpec), C.POINTER(_vp)]),
@@ -115,3 +117,18 @@ def launch_count():
 
 def last_op_device_ms():
     return float(lib.otslam_last_op_device_ms())
+
+
+def pinned_empty(shape, dtype):
+    """NumPy array over page-locked host memory (freed with the array); ordinary pageable memory when no CUDA
+    device is usable (only the copy speed differs)."""
+    import weakref
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape)) * dt.itemsize
+    p = C.c_void_p()
+    if lib.otslam_host_alloc(n, C.byref(p)) != OK or not p.value:
+        return np.empty(shape, dt)
+    buf = (C.c_uint8 * max(n, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
+    weakref.finalize(buf, lib.otslam_host_free, C.c_void_p(p.value))
+    return arr

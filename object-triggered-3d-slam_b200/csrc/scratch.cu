@@ -100,6 +100,18 @@ void scratch_free(void* p) {
 
 }  // namespace otslam
 
+extern "C" int otslam_host_alloc(uint64_t bytes, void** out) {
+    if (!out) return otslam::set_error(OTSLAM_ERR_INVALID, "null output");
+    *out = nullptr;
+    OT_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+    return OTSLAM_OK;
+}
+
+extern "C" int otslam_host_free(void* p) {
+    if (p) OT_CUDA(cudaFreeHost(p));
+    return OTSLAM_OK;
+}
+
 extern "C" int otslam_trim_scratch(void) {
     std::lock_guard<std::mutex> lk(otslam::g_mu);
     for (auto& kv : otslam::g_cache) otslam::trim_locked(kv.first, 0);

@@ -38,56 +38,130 @@ def _decode_workers():
     return max(1, min(16, int(os.environ.get("OTSLAM_DECODE_THREADS", "0")) or (os.cpu_count() or 1)))
 
 
-def _try_load(triple, intrinsics, T_fix):
+def read_pose(path):
+    """np.loadtxt(pose_path) for the 4x4 text the capture nodes write (scanner_node.cpp:294-298), without loadtxt's
+    ~0.3 ms of interpreter time per file (it runs under the GIL and capped the threaded decode).  Same correctly
+    rounded decimal -> binary64 conversion; anything but 16 plain numbers goes through np.loadtxt itself."""
+    try:
+        with open(path) as f:
+            txt = f.read()
+        vals = txt.split()
+        if len(vals) == 16 and "#" not in txt and "," not in txt:
+            return np.array([float(v) for v in vals], np.float64).reshape(4, 4)
+    except (OSError, ValueError):
+        pass
+    return np.loadtxt(path)
+
+
+def _decode_into(triple, intrinsics, T_fix, depth_out, color_out):
+    """load_frame, decoding straight into one slot of the chunk's staging buffers (no per-frame arrays, no np.stack)."""
+    import cv2
     cp, dp, pp, _ = triple
     try:
-        return load_frame(cp, dp, pp, intrinsics, T_fix), None
+        c = cv2.imread(cp, cv2.IMREAD_UNCHANGED) if os.path.exists(cp) else None
+        d = cv2.imread(dp, cv2.IMREAD_UNCHANGED) if os.path.exists(dp) else None
+        for path, a in ((cp, c), (dp, d)):
+            if a is None:
+                print(f"[Open3D WARNING] Read image failed: unable to open file: {path}")
+        pose_ros = read_pose(pp)
+        extrinsic = np.linalg.inv(pose_ros @ T_fix)
+        if c is None or d is None or c.size == 0 or d.size == 0 or c.shape[:2] != d.shape[:2]:
+            raise RuntimeError("[CreateFromColorAndDepth] Unsupported image format.")
+        if d.ndim != 2 or d.dtype != np.uint16 or c.ndim != 3 or c.shape[2] not in (3, 4) or c.dtype != np.uint8 \
+                or d.shape != (intrinsics.height, intrinsics.width):
+            raise RuntimeError(_FMT)
+        cv2.cvtColor(c, cv2.COLOR_BGRA2RGB if c.shape[2] == 4 else cv2.COLOR_BGR2RGB, dst=color_out)
+        np.copyto(depth_out, d)
+        return extrinsic, None
     except Exception as err:  # noqa: BLE001
         return None, err
+
+
+class _Staging:
+    """Two sets of chunk buffers in page-locked memory: chunk k+1 is decoded into one while chunk k is copied to the GPU
+    from the other.  Page-locking costs ~0.3 ms per MB, so the buffers are kept for the life of the process (one
+    per image size, grown on demand) and shared by every integrate_files call of the thread that owns them."""
+
+    _free = {}          # (height, width) -> idle staging objects
+    _lock = None
+
+    def __init__(self, frames, height, width, n_sets):
+        from . import _lib
+        self.frames, self.key = frames, (height, width)
+        self.sets = [(_lib.pinned_empty((frames, height, width), np.uint16), _lib.pinned_empty((frames, height, width, 3), np.uint8))
+                     for _ in range(n_sets)]
+
+    @classmethod
+    def acquire(cls, frames, height, width, n_sets):
+        import threading
+        if cls._lock is None:
+            cls._lock = threading.Lock()
+        with cls._lock:
+            idle = cls._free.setdefault((height, width), [])
+            for i, st in enumerate(idle):
+                if st.frames >= frames and len(st.sets) >= n_sets:
+                    return idle.pop(i)
+            idle.clear()                                      # too small: drop them, allocate the larger one
+        return cls(frames, height, width, n_sets)
+
+    def release(self):
+        with _Staging._lock:
+            _Staging._free.setdefault(self.key, []).append(self)
 
 
 def integrate_files(volume, triples, intrinsics, T_fix, depth_scale=1000.0, depth_trunc=3.0, skip_errors=False,
                     progress=None, on_error=None):
     """Integrate capture triples [(color, depth, pose, label)] in order. Returns frames integrated.
 
-    JPEG / PNG decoding is what bounds this loop once integration runs on the GPU (~5 ms per frame pair on
-    one core against ~0.02 ms of GPU work), so the files of a chunk are decoded by a thread pool (OpenCV
-    releases the GIL) and chunk k+1 is decoded while the GPU integrates chunk k (the C-ABI call releases the
-    GIL as well).  Results are consumed in file order, so the per-frame semantics -- abort on the first bad
-    frame, or print-and-skip -- and the frame order seen by the volume are exactly the sequential loop's."""
+    JPEG / PNG decoding is what bounds this loop once integration runs on the GPU (~6 ms per frame pair on one
+    core against ~0.02 ms of GPU work), so the files of a chunk are decoded by a thread pool (OpenCV releases the
+    GIL) straight into page-locked chunk buffers, and chunk k+1 is decoded while the GPU integrates chunk k (the
+    C-ABI call releases the GIL as well).  Results are consumed in file order, so the per-frame semantics -- abort
+    on the first bad frame, or print-and-skip -- and the frame order seen by the volume are exactly the
+    sequential loop's."""
     from concurrent.futures import ThreadPoolExecutor
     done = 0
     n = len(triples)
     chunks = [triples[c0:c0 + CHUNK_FRAMES] for c0 in range(0, n, CHUNK_FRAMES)]
     if not chunks:
         return 0
-    with ThreadPoolExecutor(max_workers=_decode_workers()) as pool:
-        def submit(chunk):
-            return [pool.submit(_try_load, t, intrinsics, T_fix) for t in chunk]
+    staging = _Staging.acquire(min(CHUNK_FRAMES, n), intrinsics.height, intrinsics.width, 2 if len(chunks) > 1 else 1)
+    try:
+        with ThreadPoolExecutor(max_workers=_decode_workers()) as pool:
+            def submit(ci):
+                dbuf, cbuf = staging.sets[ci & 1 if len(staging.sets) > 1 else 0]
+                return [pool.submit(_decode_into, t, intrinsics, T_fix, dbuf[k], cbuf[k]) for k, t in enumerate(chunks[ci])]
 
-        pending = submit(chunks[0])
-        for ci, chunk in enumerate(chunks):
-            futures = pending
-            cols, deps, exts = [], [], []
-            for k, (fut, triple) in enumerate(zip(futures, chunk)):
-                frame, err = fut.result()
-                label = triple[3]
-                if err is not None:
-                    if not skip_errors:
-                        for f in futures[k + 1:]:
-                            f.cancel()
-                        raise err
-                    if on_error:
-                        on_error(label, err)
-                    continue
-                c, d, e = frame
-                cols.append(c); deps.append(d); exts.append(e)
-                if progress:
-                    progress(label, ci * CHUNK_FRAMES + k + 1, n)
-            pending = submit(chunks[ci + 1]) if ci + 1 < len(chunks) else []     # decoded while this chunk integrates
-            if exts:
-                volume.integrate_sequence(np.stack(deps), np.stack(cols), intrinsics, np.stack(exts), depth_scale, depth_trunc)
-                done += len(exts)
+            pending = submit(0)
+            for ci, chunk in enumerate(chunks):
+                futures = pending
+                dbuf, cbuf = staging.sets[ci & 1 if len(staging.sets) > 1 else 0]
+                slots, exts = [], []
+                for k, (fut, triple) in enumerate(zip(futures, chunk)):
+                    ext, err = fut.result()
+                    label = triple[3]
+                    if err is not None:
+                        if not skip_errors:
+                            for f in futures[k + 1:]:
+                                f.cancel()
+                            raise err
+                        if on_error:
+                            on_error(label, err)
+                        continue
+                    slots.append(k); exts.append(ext)
+                    if progress:
+                        progress(label, ci * CHUNK_FRAMES + k + 1, n)
+                pending = submit(ci + 1) if ci + 1 < len(chunks) else []     # decoded while this chunk integrates
+                if exts:
+                    m = len(slots)
+                    if slots == list(range(m)):
+                        deps, cols = dbuf[:m], cbuf[:m]
+                    else:                                                     # skipped frames left holes: close them up
+                        deps, cols = np.ascontiguousarray(dbuf[slots]), np.ascontiguousarray(cbuf[slots])
+                    volume.integrate_sequence(deps, cols, intrinsics, np.stack(exts), depth_scale, depth_trunc)
+                    done += m
+    finally:
+        staging.release()
     return done
 
 

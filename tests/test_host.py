@@ -184,6 +184,28 @@ def test_integrate_files_threaded_decode_keeps_file_order(tmp_path, monkeypatch)
     assert [p[0] for p in prog] == [i for i in range(1, 12) if i not in (3, 8)] and prog[-1][1:] == (11, 11)
 
 
+def test_read_pose_equals_loadtxt(tmp_path):
+    """The pose parser of the threaded loop must give np.loadtxt's bits (reconstruct_rgbd.py:90 uses loadtxt)."""
+    from otslam_b200 import capture
+    rng = np.random.default_rng(0)
+    for k in range(50):
+        T = rng.normal(size=(4, 4)) * 10.0 ** rng.integers(-3, 4)
+        p = tmp_path / f"p{k}.txt"
+        if k % 3 == 0:
+            p.write_text(capture.pose_text(T))                          # what the capture nodes write (fixed, 6 decimals)
+        elif k % 3 == 1:
+            np.savetxt(p, T)                                            # scientific notation, 18 digits
+        else:
+            p.write_text("\n".join(" ".join(repr(float(x)) for x in r) for r in T) + "\n")
+        a, b = pipeline.read_pose(str(p)), np.loadtxt(str(p))
+        assert a.shape == (4, 4) and (a.view(np.int64) == b.view(np.int64)).all()
+    c = tmp_path / "commented.txt"
+    c.write_text("# pose\n" + capture.pose_text(np.eye(4)))                # anything unusual goes through loadtxt itself
+    assert (pipeline.read_pose(str(c)) == np.eye(4)).all()
+    with pytest.raises(Exception):
+        pipeline.read_pose(str(tmp_path / "missing.txt"))
+
+
 def test_synth_matches_capture_contract():
     seq = synth.make_sequence("table", 300, subsample=(0, 150))
     d, c = seq.numpy()
