@@ -285,7 +285,7 @@ def files_e2e(a, seq, n_files=128):
         seq_decode_fps = 32 / (time.perf_counter() - t0)
         vol = o3d.pipelines.integration.ScalableTSDFVolume(voxel_length=a.voxel, sdf_trunc=4 * a.voxel,
                                                            color_type=o3d.pipelines.integration.TSDFVolumeColorType.RGB8)
-        pipeline.integrate_files(vol, triples[:32], intr, synth.T_FIX)           # warm
+        pipeline.integrate_files(vol, triples, intr, synth.T_FIX)                # warm (file cache, staging buffers, pool growth)
         vol.reset()
         t0 = time.perf_counter()
         done = pipeline.integrate_files(vol, triples, intr, synth.T_FIX)

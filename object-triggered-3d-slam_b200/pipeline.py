@@ -78,17 +78,17 @@ def _decode_into(triple, intrinsics, T_fix, depth_out, color_out):
 
 
 class _Staging:
-    """Two sets of chunk buffers in page-locked memory: chunk k+1 is decoded into one while chunk k is copied to the GPU
-    from the other.  Page-locking costs ~0.3 ms per MB, so the buffers are kept for the life of the process (one
-    per image size, grown on demand) and shared by every integrate_files call of the thread that owns them."""
+    """Two sets of chunk buffers: chunk k+1 is decoded into one while chunk k is copied to the GPU from the other.
+    Kept in a pool for the life of the process (first-touch page faults are not free either).  Ordinary pageable
+    memory on purpose: page-locking 2 x 390 MB costs ~0.5 s up front (measured: it halved the throughput of a
+    128-frame run), while the copy of a decoded chunk is three orders of magnitude faster than decoding it."""
 
     _free = {}          # (height, width) -> idle staging objects
     _lock = None
 
     def __init__(self, frames, height, width, n_sets):
-        from . import _lib
         self.frames, self.key = frames, (height, width)
-        self.sets = [(_lib.pinned_empty((frames, height, width), np.uint16), _lib.pinned_empty((frames, height, width, 3), np.uint8))
+        self.sets = [(np.empty((frames, height, width), np.uint16), np.empty((frames, height, width, 3), np.uint8))
                      for _ in range(n_sets)]
 
     @classmethod
@@ -115,7 +115,7 @@ def integrate_files(volume, triples, intrinsics, T_fix, depth_scale=1000.0, dept
 
     JPEG / PNG decoding is what bounds this loop once integration runs on the GPU (~6 ms per frame pair on one
     core against ~0.02 ms of GPU work), so the files of a chunk are decoded by a thread pool (OpenCV releases the
-    GIL) straight into page-locked chunk buffers, and chunk k+1 is decoded while the GPU integrates chunk k (the
+    GIL) straight into pooled chunk buffers, and chunk k+1 is decoded while the GPU integrates chunk k (the
     C-ABI call releases the GIL as well).  Results are consumed in file order, so the per-frame semantics -- abort
     on the first bad frame, or print-and-skip -- and the frame order seen by the volume are exactly the
     sequential loop's."""
