@@ -52,3 +52,15 @@ def test_gpu_matches_golden():
     pts, pcols, pek = v.extract_point_cloud()
     po = mg.lexorder(pek)
     assert len(pts) == exp["pc_n"] and mg.digest(pek[po]) == exp["pc_ekeys"] and mg.digest(pts[po]) == exp["pc_pts"]
+    # post stage pins (voxel_down_sample, remove_statistical_outlier, transform) on the canonically ordered cloud
+    import otslam_b200.o3d_compat as o3d
+    pc = o3d.geometry.PointCloud()
+    pc.points, pc.colors = np.ascontiguousarray(pts[po]), np.ascontiguousarray(pcols[po])
+    ds = pc.voxel_down_sample(2.5 * float(z["voxel"][0]))
+    assert len(ds.points) == exp["vds_n"]
+    assert mg.digest(np.asarray(ds.points)) == exp["vds_pts"]      # (colours: exact integer sums here vs the FP64 running mean, <= 1e-9 apart)
+    _, idx = pc.remove_statistical_outlier(20, 2.0)
+    assert len(idx) == exp["sor_n"] and mg.digest(np.asarray(idx, np.int64)) == exp["sor_idx"]
+    moved = o3d.geometry.PointCloud(np.ascontiguousarray(pts[po])).transform(mg.POST_T)
+    assert mg.digest(np.asarray(moved.points)) == exp["xform_pts"]
+

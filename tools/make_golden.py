@@ -23,6 +23,10 @@ def lexorder(k):
     return np.lexsort(tuple(k[:, i] for i in range(k.shape[1] - 1, -1, -1)))
 
 
+_c, _s = np.cos(0.3), np.sin(0.3)
+POST_T = np.array([[_c, -_s, 0.0, 0.05], [_s, _c, 0.0, -0.1], [0.0, 0.0, 1.0, 0.2], [0.0, 0.0, 0.0, 1.0]])
+
+
 def compute(depth, rgb, intr, extr, vl, trunc):
     v = oracle.Volume(vl, trunc)
     nupd = []
@@ -33,7 +37,14 @@ def compute(depth, rgb, intr, extr, vl, trunc):
     o = lexorder(ek)
     pts, pcols, pek = v.extract_point_cloud()
     po = lexorder(pek)
+    # post stage on the canonically ordered extracted cloud (K10 / K11 / K15): order-dependent sums see the same order
+    cp, cc = np.ascontiguousarray(pts[po]), np.ascontiguousarray(pcols[po])
+    vp, vc, vk, vn = oracle.voxel_down_sample(cp, cc, 2.5 * vl)
+    kept, _ = oracle.remove_statistical_outlier(cp, 20, 2.0)
+    tp, _ = oracle.transform(cp, None, POST_T)
     return {
+        "vds_n": int(len(vp)), "vds_pts": digest(vp), "vds_cols": digest(vc), "vds_counts": digest(vn.astype(np.int32)),
+        "sor_n": int(len(kept)), "sor_idx": digest(np.asarray(kept, np.int64)), "xform_pts": digest(tp),
         "n_blocks": int(len(keys)), "touched_updated": [[int(a), int(b)] for a, b in nupd],
         "keys": digest(keys), "weight": digest(w.astype(np.uint16)), "tsdf": digest(tsdf),
         "color_u8": digest(np.floor(col + 0.5).astype(np.uint8)),
