@@ -68,6 +68,25 @@ def workload_name(a):
             f"depth_trunc 3 m, voxel {a.voxel*1000:g} mm / trunc {4*a.voxel*1000:g} mm")
 
 
+def config_of(a, world):
+    """The `config` object: a function of the command line only, so the reference arm and ours print the same one."""
+    W, H = (1280, 720) if a.hd else (640, 480)
+    par = "single GPU" if world == 1 else (
+        f"{['x-axis', 'y-axis', 'z-axis', 'diagonal (kx+ky)'][a.slab_axis]} slabs of {a.slab_thickness} block(s), cyclic over {world} ranks, " +
+        ("+1 block halo integrated redundantly" if a.slab_halo else "owned blocks only; boundary planes exchanged once before extraction"))
+    return {"workload": workload_name(a), "frames_per_step": a.frames, "frames_per_launch": a.batch, "width": W, "height": H,
+            "voxel_mm": a.voxel * 1000, "trunc_mm": 4 * a.voxel * 1000, "parallelism": par,
+            "l2": "inputs (%.0f MB per step) exceed the 126 MB L2; no flush needed" % (a.frames * W * H * 5 / 1e6)}
+
+
+def host_cores():
+    """Host threads this process may use (affinity-aware); torchrun's OMP_NUM_THREADS=1 is deliberately ignored."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:  # noqa: BLE001
+        return max(1, os.cpu_count() or 1)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -128,12 +147,20 @@ def cpu_sample(a, seq_np, budget_s=12.0):
     """Time the oracle on a bounded sample of the same sequence: frames k, k+8, k+16, ... (each
     sub-pass covers the whole trajectory), then k+1, k+9, ... into the same volume, until ~budget_s
     of CPU work (or --cpu-frames frames) is done; wraps around for sequences shorter than the budget."""
-    from oracle import oracle
+    from oracle import open3d_ref, oracle
     depth, rgb, extr, fxfycxcy = seq_np
     n = len(depth)
-    cores = oracle.num_threads()
+    cores = oracle.set_num_threads(host_cores())
     stride = 8 if n >= 64 else 1
     order = [k for off in range(stride) for k in range(off, n, stride)]
+    sample = (f"frames of the {n}-frame sequence (every {stride}th frame, then the next offset, ...) into one volume "
+              f"(depth convert + allocate + integrate per frame)")
+    if open3d_ref.available() and not os.environ.get("OTSLAM_BENCH_NO_OPEN3D"):
+        # the real backend of the reference (reconstruct_rgbd.py:99-107), same frames, same order
+        H, W = depth.shape[1:]
+        done, dt = open3d_ref.time_frame_loop(depth, rgb, (W, H) + tuple(fxfycxcy), extr, a.voxel, 4 * a.voxel, budget_s, order)
+        return {"value": done / dt, "unit": UNIT, "cores": cores, "kind": "reference", "backend": "open3d " + open3d_ref.version(),
+                "sample": f"{done} {sample}, {dt:.1f} s of CPU work, Open3D's own OpenMP threading on {cores} host threads"}, dt, done
     vol = oracle.Volume(a.voxel, 4 * a.voxel)
     done = 0
     t0 = time.perf_counter()
@@ -145,8 +172,51 @@ def cpu_sample(a, seq_np, budget_s=12.0):
         if (a.cpu_frames and done >= a.cpu_frames) or (not a.cpu_frames and dt >= budget_s) or done >= 64 * n:
             break
     return {"value": done / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{done} frames of the {n}-frame sequence (every {stride}th frame, then the next offset, ...) into one "
-                      f"volume (depth convert + allocate + integrate per frame), {dt:.1f} s of CPU work on {cores} threads"}, dt, done
+            "sample": f"{done} {sample}, {dt:.1f} s of CPU work on {cores} threads"}, dt, done
+
+
+def cpu_full_loop(a, seq, n_files=48, budget_s=6.0):
+    """The reference's WHOLE per-frame loop on the host (reconstruct_rgbd.py:86-109): read_image x2 (JPEG + 16-bit PNG
+    decode), np.loadtxt, pose @ T_fix, np.linalg.inv, create_from_color_and_depth, integrate -- sequential, as the script
+    runs it, from a capture tree written in scanner_node.cpp's format.  Integration uses all host threads (oracle port, or
+    open3d when importable); decoding is single-threaded like the reference's."""
+    import shutil
+    import tempfile
+    import cv2
+    import numpy as np
+    from oracle import open3d_ref, oracle
+    from otslam_b200 import capture, synth
+    depth, rgb = seq.numpy()
+    n = min(n_files, len(seq))
+    idx = [int(i) for i in range(0, len(seq), max(1, len(seq) // n))][:n]
+    base = tempfile.mkdtemp(prefix="otslam_cpu_loop_")
+    cores = oracle.set_num_threads(host_cores())
+    use_o3d = open3d_ref.available() and not os.environ.get("OTSLAM_BENCH_NO_OPEN3D")
+    try:
+        for j, k in enumerate(idx):
+            capture.save_frame(base, "Object_0", j + 1, rgb[k], depth[k], seq.pose_ros[k])
+        H, W = depth.shape[1:]
+        vol = open3d_ref.make_volume(a.voxel, 4 * a.voxel) if use_o3d else oracle.Volume(a.voxel, 4 * a.voxel)
+        intr = open3d_ref.intrinsic(W, H, *seq.fxfycxcy) if use_o3d else None
+        done, t0 = 0, time.perf_counter()
+        while True:
+            j = done % n + 1
+            col = cv2.cvtColor(cv2.imread(os.path.join(base, "color", f"Object_0_{j}.jpg"), cv2.IMREAD_UNCHANGED), cv2.COLOR_BGR2RGB)
+            dep = cv2.imread(os.path.join(base, "depth", f"Object_0_{j}.png"), cv2.IMREAD_UNCHANGED)
+            pose_ros = np.loadtxt(os.path.join(base, "poses", f"Object_0_{j}.txt"))
+            extrinsic = np.linalg.inv(pose_ros @ synth.T_FIX)
+            if use_o3d:
+                open3d_ref.integrate(vol, dep, col, intr, extrinsic)
+            else:
+                vol.integrate(oracle.depth_convert(dep, 1000.0, 3.0), col, seq.fxfycxcy, extrinsic)
+            done += 1
+            dt = time.perf_counter() - t0
+            if dt >= budget_s or done >= 16 * n:
+                break
+        return {"value": done / dt, "unit": UNIT, "cores": cores, "kind": "reference" if use_o3d else "port",
+                "sample": f"{done} frames ({n} distinct capture triples) decoded + integrated sequentially in {dt:.1f} s"}
+    finally:
+        shutil.rmtree(base, ignore_errors=True)
 
 
 def post_stage(a, vol, n_blocks, peak):
@@ -322,11 +392,16 @@ def run_reference(a):
     tot_f = sum(v[0] for v in vals); tot_t = sum(v[1] for v in vals)
     value = tot_f / tot_t
     res["value"] = value
+    try:
+        res["full_loop"] = cpu_full_loop(a, seq)
+    except Exception as e:  # noqa: BLE001 -- informational
+        res["full_loop"] = {"error": repr(e)}
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": 1e3 * tot_t / max(1, a.steps), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(a), "note": "reference CPU path = oracle port of Open3D legacy "
-                       "ScalableTSDFVolume (open3d itself is not installable offline); each step is a bounded sample"},
+            "config": config_of(a, max(1, a.gpus)),
+            "reference_note": ("reference CPU path = " + (res.get("backend") or "oracle port of Open3D legacy ScalableTSDFVolume "
+                               "(open3d itself is not installable offline)") + "; each step is a bounded sample of the workload"),
             "cpu_baseline": res,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -497,14 +572,8 @@ def run_ours(a):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload_name(a), "frames_per_step": n, "frames_per_launch": a.batch,
-                           "parallelism": "single GPU" if world == 1 else (
-                               f"{['x-axis', 'y-axis', 'z-axis', 'diagonal (kx+ky)'][a.slab_axis]} slabs of {a.slab_thickness} block(s), cyclic over {world} ranks, " +
-                               ("+1 block halo integrated redundantly" if a.slab_halo else
-                                "owned blocks only; boundary planes exchanged once before extraction")),
-                           "l2": "inputs (%.0f MB) + volume (%.0f MB) exceed the 126 MB L2; no flush needed" % (
-                               n * W * H * 5 / 1e6, stats["n_blocks"] * 65536 / 1e6),
-                           "n_blocks": stats["n_blocks"]},
+                "config": config_of(a, world), "n_blocks": stats["n_blocks"],
+                "volume_mb": stats["n_blocks"] * 65536 / 1e6,
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "post_stage": post, "gpu_launches": int(launches),
                 "clocks": clocks, "achieved_hbm_gbs_whole_step": bytes_step * a.steps / (ms_max * 1e-3) / 1e9}
         line.update(extra)

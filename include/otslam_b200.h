@@ -79,6 +79,11 @@ int otslam_volume_destroy(otslam_volume* v);
 int otslam_volume_reset(otslam_volume* v);                       /* ScalableTSDFVolume.reset() */
 /* run this volume's kernels on a caller-owned cudaStream_t (e.g. torch's current stream) */
 int otslam_volume_set_stream(otslam_volume* v, void* cuda_stream);
+/* Stream contract for DEVICE buffers (OTSLAM_MEM_DEVICE frames, device halo pieces): the volume works on its own
+ * non-blocking streams, so buffers produced on another stream (a torch stream, an NCCL collective) must either be
+ * complete (that stream synchronised) or ordered with this call: everything queued on `producer_stream` (NULL = the
+ * legacy default stream) so far will finish before any work the volume queues afterwards. */
+int otslam_volume_wait_stream(otslam_volume* v, void* producer_stream);
 /* frames fused per block residency in integrate_batch (1..32, default 32) */
 int otslam_volume_set_batch(otslam_volume* v, int frames_per_batch);
 
@@ -126,7 +131,15 @@ int otslam_volume_stats(otslam_volume* v, int64_t* n_blocks, uint64_t* weight_su
  *      of the -x / -y neighbours and the column to the owner of the -x-y neighbour.  import inserts received
  *      pieces into (non-owned) blocks.  Call export with NULL buffers to get the count. */
 int otslam_volume_halo_export(otslam_volume* v, int64_t* n, int32_t* keys, int32_t* dest_rank, void* planes);
+/* keys / planes may be HOST or DEVICE pointers (unified addressing); device sources must be complete on the volume's
+ * stream (otslam_volume_wait_stream) or on a synchronised stream */
 int otslam_volume_halo_import(otslam_volume* v, int64_t n, const int32_t* keys, const void* planes);
+/* The device-resident form of the export, for the NCCL exchange (no host copy of voxel data): pack selects and packs the
+ * pieces inside HBM, grouped by destination rank ((key, kind) order inside a group) and returns the total and the
+ * per-destination counts (counts_per_rank [n_ranks], nullable); fetch copies the packed keys [n][4] / planes [n][4096]
+ * into caller buffers, which may be DEVICE pointers (e.g. torch CUDA tensors handed to ncclSend) or host pointers. */
+int otslam_volume_halo_pack(otslam_volume* v, int64_t* n_pieces, int64_t* counts_per_rank);
+int otslam_volume_halo_fetch(otslam_volume* v, int32_t* keys, void* planes);
 
 /* ---- surface extraction: volume.extract_triangle_mesh() (reconstruct_rgbd.py:112) followed by
  *      mesh.compute_vertex_normals() (reconstruct_rgbd.py:113).  extract runs the kernels and
@@ -134,7 +147,7 @@ int otslam_volume_halo_import(otslam_volume* v, int64_t n, const int32_t* keys, 
  *      + axis of each vertex's lattice edge (canonical order for comparisons); nullable outputs. */
 int otslam_volume_extract_mesh(otslam_volume* v, int64_t* n_vertices, int64_t* n_faces);
 int otslam_volume_mesh_copy(otslam_volume* v, double* vertices, double* colors, double* normals, int32_t* faces,
-                            int32_t* edge_keys);
+                            int32_t* edge_keys);   /* destinations: host or device pointers */
 /* mesh.sample_points_uniformly(n) (reconstruct_rgbd_filter.py:123) straight from the mesh the last
  * otslam_volume_extract_mesh left in HBM: no download + re-upload of the (often ~100 MB) mesh when the
  * caller only wants the samples.  Same arithmetic and sample order as otslam_mesh_sample_uniform;
@@ -143,7 +156,7 @@ int otslam_volume_mesh_sample(otslam_volume* v, int64_t n_samples, uint64_t seed
                               double* out_colors, double* out_normals);
 /* volume.extract_point_cloud() (named by north_star; zero crossings along +x/+y/+z) */
 int otslam_volume_extract_points(otslam_volume* v, int64_t* n_points);
-int otslam_volume_points_copy(otslam_volume* v, double* points, double* colors, int32_t* edge_keys);
+int otslam_volume_points_copy(otslam_volume* v, double* points, double* colors, int32_t* edge_keys);   /* host or device */
 
 /* ---- stateless image / cloud operators (host in, host out) */
 /* RGBDImage.create_from_color_and_depth depth half (reconstruct_rgbd.py:99-104) */

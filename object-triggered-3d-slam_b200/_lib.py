@@ -54,6 +54,9 @@ _SIGS = {
     "otslam_volume_stats": (_i, [_vp, C.POINTER(_i64), C.POINTER(_u64), C.POINTER(_u64)]),
     "otslam_volume_halo_export": (_i, [_vp, C.POINTER(_i64), _vp, _vp, _vp]),
     "otslam_volume_halo_import": (_i, [_vp, _i64, _vp, _vp]),
+    "otslam_volume_halo_pack": (_i, [_vp, C.POINTER(_i64), _vp]),
+    "otslam_volume_halo_fetch": (_i, [_vp, _vp, _vp]),
+    "otslam_volume_wait_stream": (_i, [_vp, _vp]),
     "otslam_volume_extract_mesh": (_i, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
     "otslam_volume_mesh_copy": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "otslam_volume_mesh_sample": (_i, [_vp, _i64, _u64, _vp, _vp, _vp]),

@@ -482,19 +482,14 @@ __global__ void __launch_bounds__(256) pc_extract_kernel(ExtractCtx c, const int
     }
 }
 
-static int make_ctx(otslam_volume* v, ExtractCtx& c, DevBuf<uint64_t>& dk, DevBuf<int32_t>& ds) {
-    std::vector<uint64_t> k;
-    std::vector<int32_t> s;
-    OT_TRY(volume_sorted_blocks(v, k, s));
-    OT_CUDA(dk.alloc(k.size()));
-    OT_CUDA(ds.alloc(s.size()));
-    if (!k.empty()) {
-        OT_CUDA(cudaMemcpyAsync(dk.p, k.data(), k.size() * 8, cudaMemcpyHostToDevice, v->stream));
-        OT_CUDA(cudaMemcpyAsync(ds.p, s.data(), s.size() * 4, cudaMemcpyHostToDevice, v->stream));
-        OT_CUDA(cudaStreamSynchronize(v->stream));
-    }
+// the sorted block list lives in HBM (volume.cu: volume_sorted_blocks_device): no host round trip of the hash table
+static int make_ctx(otslam_volume* v, ExtractCtx& c) {
+    const uint64_t* dk = nullptr;
+    const int32_t* ds = nullptr;
+    int n = 0;
+    OT_TRY(volume_sorted_blocks_device(v, &dk, &ds, &n));
     c.keys = v->d_keys; c.vals = v->d_vals; c.cap_mask = v->cap - 1; c.chunks = v->d_chunks;
-    c.bkeys = dk.p; c.bslots = ds.p; c.n = (int)k.size(); c.slab = v->slab;
+    c.bkeys = dk; c.bslots = ds; c.n = n; c.slab = v->slab;
     c.vl = v->voxel_length; c.half = 0.5 * v->voxel_length;
     return OTSLAM_OK;
 }
@@ -513,9 +508,7 @@ int otslam_volume_extract_mesh(otslam_volume* v, int64_t* n_vertices, int64_t* n
     *n_vertices = 0; *n_faces = 0;
     OpTimer timer(v->stream);
     ExtractCtx c;
-    DevBuf<uint64_t> dk;
-    DevBuf<int32_t> ds;
-    OT_TRY(make_ctx(v, c, dk, ds));
+    OT_TRY(make_ctx(v, c));
     const int n = c.n;
     if (n == 0) return OTSLAM_OK;
     cudaStream_t s = v->stream;
@@ -570,12 +563,13 @@ int otslam_volume_mesh_copy(otslam_volume* v, double* vertices, double* colors, 
     OT_TRY(use_device(v->device));
     const MeshResult& m = v->mesh;
     if (m.nv > 0) {
-        if (vertices) OT_CUDA(cudaMemcpy(vertices, m.d_verts, (size_t)m.nv * 24, cudaMemcpyDeviceToHost));
-        if (colors) OT_CUDA(cudaMemcpy(colors, m.d_colors, (size_t)m.nv * 24, cudaMemcpyDeviceToHost));
-        if (normals) OT_CUDA(cudaMemcpy(normals, m.d_normals, (size_t)m.nv * 24, cudaMemcpyDeviceToHost));
-        if (edge_keys) OT_CUDA(cudaMemcpy(edge_keys, m.d_ekeys, (size_t)m.nv * 16, cudaMemcpyDeviceToHost));
+        if (vertices) OT_CUDA(cudaMemcpyAsync(vertices, m.d_verts, (size_t)m.nv * 24, cudaMemcpyDefault, v->stream));
+        if (colors) OT_CUDA(cudaMemcpyAsync(colors, m.d_colors, (size_t)m.nv * 24, cudaMemcpyDefault, v->stream));
+        if (normals) OT_CUDA(cudaMemcpyAsync(normals, m.d_normals, (size_t)m.nv * 24, cudaMemcpyDefault, v->stream));
+        if (edge_keys) OT_CUDA(cudaMemcpyAsync(edge_keys, m.d_ekeys, (size_t)m.nv * 16, cudaMemcpyDefault, v->stream));
     }
-    if (m.nf > 0 && faces) OT_CUDA(cudaMemcpy(faces, m.d_faces, (size_t)m.nf * 12, cudaMemcpyDeviceToHost));
+    if (m.nf > 0 && faces) OT_CUDA(cudaMemcpyAsync(faces, m.d_faces, (size_t)m.nf * 12, cudaMemcpyDefault, v->stream));
+    OT_CUDA(cudaStreamSynchronize(v->stream));     // destinations may be host or device pointers (unified addressing)
     return OTSLAM_OK;
 }
 
@@ -586,9 +580,7 @@ int otslam_volume_extract_points(otslam_volume* v, int64_t* n_points) {
     *n_points = 0;
     OpTimer timer(v->stream);
     ExtractCtx c;
-    DevBuf<uint64_t> dk;
-    DevBuf<int32_t> ds;
-    OT_TRY(make_ctx(v, c, dk, ds));
+    OT_TRY(make_ctx(v, c));
     const int n = c.n;
     if (n == 0) return OTSLAM_OK;
     cudaStream_t s = v->stream;
@@ -620,9 +612,10 @@ int otslam_volume_points_copy(otslam_volume* v, double* points, double* colors, 
     OT_TRY(use_device(v->device));
     const PointsResult& p = v->points;
     if (p.n > 0) {
-        if (points) OT_CUDA(cudaMemcpy(points, p.d_pts, (size_t)p.n * 24, cudaMemcpyDeviceToHost));
-        if (colors) OT_CUDA(cudaMemcpy(colors, p.d_cols, (size_t)p.n * 24, cudaMemcpyDeviceToHost));
-        if (edge_keys) OT_CUDA(cudaMemcpy(edge_keys, p.d_ekeys, (size_t)p.n * 16, cudaMemcpyDeviceToHost));
+        if (points) OT_CUDA(cudaMemcpyAsync(points, p.d_pts, (size_t)p.n * 24, cudaMemcpyDefault, v->stream));
+        if (colors) OT_CUDA(cudaMemcpyAsync(colors, p.d_cols, (size_t)p.n * 24, cudaMemcpyDefault, v->stream));
+        if (edge_keys) OT_CUDA(cudaMemcpyAsync(edge_keys, p.d_ekeys, (size_t)p.n * 16, cudaMemcpyDefault, v->stream));
+        OT_CUDA(cudaStreamSynchronize(v->stream));
     }
     return OTSLAM_OK;
 }

@@ -170,31 +170,37 @@ __global__ void __launch_bounds__(256) radix_scatter_kernel(const uint64_t* __re
     }
 }
 
-// sorts by the low `bits` bits of the keys; result ends up in (k_out, v_out)
-static int sort_pairs(DevBuf<uint64_t>& k_in, DevBuf<int32_t>& v_in, DevBuf<uint64_t>& k_out, DevBuf<int32_t>& v_out, int64_t n,
-                      int bits) {
+// sorts by the low `bits` bits of the keys on stream s; the result ends up in (kb, vb); (ka, va) are clobbered
+int device_sort_pairs(uint64_t* ka_in, int32_t* va_in, uint64_t* kb_out, int32_t* vb_out, int64_t n, int bits, cudaStream_t s) {
+    if (n <= 0) return OTSLAM_OK;
     const int n_cta = (int)((n + kSortTile - 1) / kSortTile);
     const int passes = std::max(1, (bits + 7) / 8);
     DevBuf<int> hist;
     DevBuf<int64_t> offs;
     OT_CUDA(hist.alloc((size_t)256 * n_cta));
     OT_CUDA(offs.alloc((size_t)256 * n_cta + 1));
-    uint64_t *ka = k_in.p, *kb = k_out.p;
-    int32_t *va = v_in.p, *vb = v_out.p;
+    uint64_t *ka = ka_in, *kb = kb_out;
+    int32_t *va = va_in, *vb = vb_out;
     for (int p = 0; p < passes; ++p) {
-        radix_hist_kernel<<<n_cta, 256>>>(ka, n, 8 * p, n_cta, hist.p);
+        radix_hist_kernel<<<n_cta, 256, 0, s>>>(ka, n, 8 * p, n_cta, hist.p);
         OT_LAUNCHED();
-        OT_TRY(device_exclusive_scan(hist.p, offs.p, 256 * n_cta, 0));   // digit-major: all tiles of digit 0, then digit 1, ...
-        radix_scatter_kernel<<<n_cta, 256>>>(ka, va, n, 8 * p, n_cta, offs.p, kb, vb);
+        OT_TRY(device_exclusive_scan(hist.p, offs.p, 256 * n_cta, s));   // digit-major: all tiles of digit 0, then digit 1, ...
+        radix_scatter_kernel<<<n_cta, 256, 0, s>>>(ka, va, n, 8 * p, n_cta, offs.p, kb, vb);
         OT_LAUNCHED();
         std::swap(ka, kb);
         std::swap(va, vb);
     }
-    if (ka != k_out.p) {   // odd number of passes leaves the result in the input buffers
-        OT_CUDA(cudaMemcpy(k_out.p, ka, (size_t)n * 8, cudaMemcpyDeviceToDevice));
-        OT_CUDA(cudaMemcpy(v_out.p, va, (size_t)n * 4, cudaMemcpyDeviceToDevice));
+    if (ka != kb_out) {   // odd number of passes leaves the result in the input buffers
+        OT_CUDA(cudaMemcpyAsync(kb_out, ka, (size_t)n * 8, cudaMemcpyDeviceToDevice, s));
+        OT_CUDA(cudaMemcpyAsync(vb_out, va, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
     }
+    // hist / offs go back to the scratch cache on return; the caller's later allocations are used on the same stream
+    // (stream order protects them) and every operator synchronises before it returns
     return OTSLAM_OK;
+}
+static int sort_pairs(DevBuf<uint64_t>& k_in, DevBuf<int32_t>& v_in, DevBuf<uint64_t>& k_out, DevBuf<int32_t>& v_out, int64_t n,
+                      int bits) {
+    return device_sort_pairs(k_in.p, v_in.p, k_out.p, v_out.p, n, bits, 0);
 }
 
 // segment heads of the sorted keys: count pass / emit pass (ordered)

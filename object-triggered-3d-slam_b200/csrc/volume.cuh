@@ -96,9 +96,28 @@ struct otslam_volume {
 
     otslam::MeshResult mesh;
     otslam::PointsResult points;
+
+    // device-resident list of the allocated blocks sorted by key (extraction order, export, halo selection); rebuilt
+    // when `epoch` (bumped by integrate / reset / halo import) has moved past `sorted_epoch`
+    uint64_t epoch = 1, sorted_epoch = 0;
+    uint64_t* d_sorted_keys = nullptr;
+    int32_t* d_sorted_slots = nullptr;
+    int64_t n_sorted = 0;
+
+    // halo pieces packed by otslam_volume_halo_pack: grouped by destination rank, (key, kind) order inside a group
+    int32_t* d_halo_keys = nullptr;      // [n_halo][4]
+    uint4* d_halo_planes = nullptr;      // [n_halo][256]
+    int64_t n_halo = 0;
+    std::vector<int64_t> halo_counts;    // pieces per destination rank
+
+    cudaEvent_t ev_ext = nullptr;        // otslam_volume_wait_stream
 };
 
 namespace otslam {
-// implemented in volume.cu, used by extract.cu
+// implemented in volume.cu, used by extract.cu: the allocated blocks sorted by key, in HBM (valid until the volume changes)
+int volume_sorted_blocks_device(otslam_volume* v, const uint64_t** d_keys, const int32_t** d_slots, int* n);
+// the same downloaded to the host (export_blocks)
 int volume_sorted_blocks(otslam_volume* v, std::vector<uint64_t>& keys, std::vector<int32_t>& slots);
+// knn.cu: stable LSD radix sort of (u64 key, i32 value) pairs by the low `bits` bits; result in (kb, vb), (ka, va) clobbered
+int device_sort_pairs(uint64_t* ka, int32_t* va, uint64_t* kb, int32_t* vb, int64_t n, int bits, cudaStream_t s);
 }

@@ -27,124 +27,162 @@ def slab_spec(rank, world, axis=0, thickness=DEFAULT_THICKNESS, halo=1):
     return (axis, thickness, world, rank) if halo else (axis, thickness, world, rank, 0)
 
 
+def _t(a, device):
+    """numpy array -> tensor on `device` (the CPU / gloo tests and host-side backends); tensors pass through."""
+    if isinstance(a, torch.Tensor):
+        return a
+    return torch.from_numpy(np.ascontiguousarray(a)).to(device)
+
+
+def _halo_pack(vol, world, device):
+    """(keys [n,4] i32, pieces [n,rec] u8, pieces per destination rank) as tensors on `device`, grouped by
+    destination.  A GPU TSDFVolume packs them inside HBM (otslam_volume_halo_pack: no host copy of voxel data);
+    host-side backends (the oracle in the gloo tests) return numpy arrays sorted by key, grouped here."""
+    if hasattr(vol, "halo_pack_tensors"):
+        keys, planes, counts = vol.halo_pack_tensors()
+        return keys, planes, [int(c) for c in counts[:world]]
+    keys, dest, planes = vol.halo_export()
+    order = np.argsort(dest, kind="stable")
+    counts = [int((dest == r).sum()) for r in range(world)]
+    planes = planes.reshape(len(keys), -1) if len(keys) else planes.reshape(0, planes.shape[1] if planes.ndim == 2 else 0)
+    return _t(keys[order], device), _t(planes[order], device), counts
+
+
 def exchange_halo(vol, rank, world, device="cpu"):
-    """halo=0 mode: send each owned boundary plane to the rank that owns the -axis neighbour block and
-    insert the received planes as non-owned blocks.  Must run after integration and before
-    extraction.  Returns the number of planes received."""
+    """halo=0 mode: send each owned boundary piece to the rank that owns the -axis neighbour block and insert the
+    received pieces as non-owned blocks.  Must run after integration and before extraction.  On GPUs the pieces
+    never leave HBM: pack kernel -> ncclSend/ncclRecv on device buffers -> import kernel.  Returns the number of
+    pieces received."""
     if world <= 1:
         return 0
-    keys, dest, planes = vol.halo_export()
-    rec = planes.shape[1] if planes.ndim == 2 else 0
-    counts = torch.tensor([int((dest == r).sum()) for r in range(world)] + [rec], dtype=torch.int64, device=device)
-    allc = [torch.zeros(world + 1, dtype=torch.int64, device=device) for _ in range(world)]
-    dist.all_gather(allc, counts)
-    allc = [[int(x) for x in c.tolist()] for c in allc]          # allc[src][dst]
-    rec = max(c[world] for c in allc)
-    ops, send_keep, recv = [], [], []
+    keys, planes, counts = _halo_pack(vol, world, device)
+    rec = int(planes.shape[1]) if planes.ndim == 2 else 0
+    mine = torch.tensor(counts + [rec], dtype=torch.int64, device=device)
+    allc = torch.empty(world * (world + 1), dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(allc, mine)
+    allc = allc.view(world, world + 1).tolist()                   # allc[src][dst]
+    rec = max(int(c[world]) for c in allc)
+    n_in = [int(allc[r][rank]) if r != rank else 0 for r in range(world)]
+    total_in = sum(n_in)
+    rk = torch.empty((total_in, 4), dtype=torch.int32, device=device)
+    rp = torch.empty((total_in, rec), dtype=torch.uint8, device=device)
+    ops, off_out, off_in = [], 0, 0
     for r in range(world):
-        if r == rank:
-            continue
-        n_out = allc[rank][r]
-        if n_out:
-            sel = dest == r
-            tk = torch.from_numpy(np.ascontiguousarray(keys[sel])).to(device)
-            tp = torch.from_numpy(np.ascontiguousarray(planes[sel])).to(device)
-            send_keep += [tk, tp]
-            ops += [dist.P2POp(dist.isend, tk, r), dist.P2POp(dist.isend, tp, r)]
-        n_in = allc[r][rank]
-        if n_in:
-            rk = torch.empty((n_in, 4), dtype=torch.int32, device=device)
-            rp = torch.empty((n_in, rec), dtype=torch.uint8, device=device)
-            recv.append((rk, rp))
-            ops += [dist.P2POp(dist.irecv, rk, r), dist.P2POp(dist.irecv, rp, r)]
+        n_out = counts[r]
+        if n_out and r != rank:
+            ops += [dist.P2POp(dist.isend, keys[off_out:off_out + n_out], r), dist.P2POp(dist.isend, planes[off_out:off_out + n_out], r)]
+        off_out += n_out
+        if n_in[r]:
+            ops += [dist.P2POp(dist.irecv, rk[off_in:off_in + n_in[r]], r), dist.P2POp(dist.irecv, rp[off_in:off_in + n_in[r]], r)]
+            off_in += n_in[r]
     if ops:
         for w in dist.batch_isend_irecv(ops):
             w.wait()
-    got = 0
-    for rk, rp in recv:
-        vol.halo_import(rk.cpu().numpy(), rp.cpu().numpy())
-        got += len(rk)
-    return got
+    if total_in:
+        if hasattr(vol, "halo_pack_tensors"):
+            vol.halo_import(rk, rp)                               # device pointers; ordered after the recv on torch's stream
+        else:
+            vol.halo_import(rk.cpu().numpy(), rp.cpu().numpy())
+    return total_in
 
 
-def _gatherv(arrays, rank, world, device):
-    """Gather a list of variable-length numpy arrays (same dtype / trailing shape on every rank) to
-    rank 0.  Returns, on rank 0, one list per input with the parts of ranks 0..world-1."""
-    counts = torch.tensor([len(a) for a in arrays], dtype=torch.int64, device=device)
-    all_counts = [torch.zeros(len(arrays), dtype=torch.int64, device=device) for _ in range(world)]
-    dist.all_gather(all_counts, counts)
-    all_counts = [[int(x) for x in c.tolist()] for c in all_counts]
-    out = [[None] * world for _ in arrays]
+def _gatherv(tensors, rank, world, device):
+    """Gather variable-length tensors (same dtype / trailing shape on every rank) to rank 0 over send/recv.  Rank 0
+    receives every part straight into its slice of one destination tensor per input (no staging, no host copy) and
+    returns (list of gathered tensors, counts[r][i]); other ranks return (None, counts)."""
+    counts = torch.tensor([int(t.shape[0]) for t in tensors], dtype=torch.int64, device=device)
+    allc = torch.empty(world * len(tensors), dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(allc, counts)
+    allc = allc.view(world, len(tensors)).tolist()
     if rank == 0:
-        ops, bufs = [], []
-        for r in range(1, world):
-            for ai, a in enumerate(arrays):
-                t = torch.empty((all_counts[r][ai],) + a.shape[1:], dtype=torch.from_numpy(a[:0]).dtype, device=device)
-                bufs.append((ai, r, t))
-                if all_counts[r][ai] > 0:
-                    ops.append(dist.P2POp(dist.irecv, t, r))
+        out, ops = [], []
+        for i, t in enumerate(tensors):
+            total = sum(int(allc[r][i]) for r in range(world))
+            dst = torch.empty((total,) + tuple(t.shape[1:]), dtype=t.dtype, device=device)
+            n0 = int(allc[0][i])
+            dst[:n0].copy_(t)
+            off = n0
+            for r in range(1, world):
+                n = int(allc[r][i])
+                if n:
+                    ops.append(dist.P2POp(dist.irecv, dst[off:off + n], r))
+                off += n
+            out.append(dst)
         if ops:
             for w in dist.batch_isend_irecv(ops):
                 w.wait()
-        for ai, a in enumerate(arrays):
-            out[ai][0] = a
-        for ai, r, t in bufs:
-            out[ai][r] = t.cpu().numpy()
-        return out
-    ops = []
-    keep = []
-    for a in arrays:
-        if len(a) > 0:
-            t = torch.from_numpy(np.ascontiguousarray(a)).to(device)
-            keep.append(t)
-            ops.append(dist.P2POp(dist.isend, t, 0))
+        return out, allc
+    ops = [dist.P2POp(dist.isend, t.contiguous(), 0) for t in tensors if t.shape[0] > 0]
     if ops:
         for w in dist.batch_isend_irecv(ops):
             w.wait()
-    return None
+    return None, allc
+
+
+def merge_mesh_tensors(verts, cols, faces, ek):
+    """Unify vertices that two ranks emitted for the same lattice edge (same edge key): returns (vertices, colors,
+    faces, edge_keys) with vertices ordered by edge key.  Tensor code, runs where the tensors live (HBM on rank 0)."""
+    if verts.shape[0] == 0:
+        return verts, cols, faces.to(torch.int32), ek
+    uniq, inverse = torch.unique(ek, dim=0, return_inverse=True)
+    inverse = inverse.reshape(-1)
+    first = torch.full((uniq.shape[0],), verts.shape[0], dtype=torch.int64, device=verts.device)
+    first.scatter_reduce_(0, inverse, torch.arange(verts.shape[0], dtype=torch.int64, device=verts.device), reduce="amin")
+    return verts[first], cols[first], inverse[faces.to(torch.int64)].to(torch.int32), uniq.to(torch.int32)
 
 
 def merge_mesh_parts(parts):
-    """Host logic of the mesh gather: concatenate per-rank (vertices, colors, faces, edge_keys),
-    rebase the face indices, and unify boundary vertices that two ranks emitted (same edge key).
-    Returns (vertices, colors, faces, edge_keys) with vertices ordered by edge key."""
-    verts = np.concatenate([p[0] for p in parts]) if parts else np.zeros((0, 3))
-    cols = np.concatenate([p[1] for p in parts]) if parts else np.zeros((0, 3))
-    ek = np.concatenate([p[3] for p in parts]) if parts else np.zeros((0, 4), np.int32)
+    """Host form of the mesh merge (numpy in / out): concatenate per-rank (vertices, colors, faces, edge_keys),
+    rebase the face indices, and unify boundary vertices that two ranks emitted (same edge key)."""
+    if not parts:
+        return np.zeros((0, 3)), np.zeros((0, 3)), np.zeros((0, 3), np.int32), np.zeros((0, 4), np.int32)
+    verts = torch.from_numpy(np.concatenate([np.asarray(p[0], np.float64).reshape(-1, 3) for p in parts]))
+    cols = torch.from_numpy(np.concatenate([np.asarray(p[1], np.float64).reshape(-1, 3) for p in parts]))
+    ek = torch.from_numpy(np.concatenate([np.asarray(p[3], np.int32).reshape(-1, 4) for p in parts]))
     faces, base = [], 0
     for p in parts:
-        faces.append(p[2].astype(np.int64) + base)
+        faces.append(np.asarray(p[2]).reshape(-1, 3).astype(np.int64) + base)
         base += len(p[0])
-    faces = np.concatenate(faces) if faces else np.zeros((0, 3), np.int64)
-    if len(verts) == 0:
-        return verts, cols, faces.astype(np.int32), ek
-    uniq, first, inverse = np.unique(ek, axis=0, return_index=True, return_inverse=True)
-    inverse = inverse.reshape(-1)
-    return verts[first], cols[first], inverse[faces].astype(np.int32), uniq.astype(np.int32)
+    faces = torch.from_numpy(np.concatenate(faces))
+    return tuple(x.numpy() for x in merge_mesh_tensors(verts, cols, faces, ek))
 
 
-def extract_and_gather_points(vol, rank, world, device="cpu"):
-    """volume.extract_point_cloud() on every rank's slab, gathered to rank 0 (None elsewhere)."""
-    pts, cols, ek = vol.extract_point_cloud()
-    if world <= 1:
-        return pts, cols, ek
-    g = _gatherv([pts, cols, ek], rank, world, device)
-    if rank != 0:
-        return None
-    return tuple(np.concatenate(x) for x in g)
+def extract_and_gather_points(vol, rank, world, device="cpu", as_numpy=True):
+    """volume.extract_point_cloud() on every rank's slab, gathered to rank 0 (None elsewhere).  With a GPU volume the
+    extracted points go HBM -> NVLink -> rank 0's HBM; as_numpy=False returns the device tensors there."""
+    if hasattr(vol, "extract_point_cloud_tensors"):
+        parts = list(vol.extract_point_cloud_tensors())
+    else:
+        parts = [_t(a, device) for a in vol.extract_point_cloud()]
+    if world > 1:
+        parts, _ = _gatherv(parts, rank, world, device)
+        if rank != 0:
+            return None
+    return tuple(p.cpu().numpy() for p in parts) if as_numpy else tuple(parts)
 
 
-def extract_and_gather_mesh(vol, rank, world, device="cpu"):
+def extract_and_gather_mesh(vol, rank, world, device="cpu", as_numpy=True):
     """volume.extract_triangle_mesh() on every rank's slab, merged on rank 0 (None elsewhere).
     Vertex normals must be recomputed on the merged mesh (they depend on faces of both sides)."""
-    r = vol.extract_triangle_mesh(normals=False) if hasattr(vol, "set_batch") else vol.extract_triangle_mesh()
-    verts, cols, faces, ek = (r[0], r[1], r[3], r[4]) if len(r) == 5 else r
-    if world <= 1:
-        return merge_mesh_parts([(verts, cols, faces, ek)])
-    g = _gatherv([verts, cols, faces, ek], rank, world, device)
-    if rank != 0:
-        return None
-    return merge_mesh_parts([(g[0][r_], g[1][r_], g[2][r_], g[3][r_]) for r_ in range(world)])
+    if hasattr(vol, "extract_mesh_tensors"):
+        verts, cols, faces, ek = vol.extract_mesh_tensors()
+    else:
+        r = vol.extract_triangle_mesh()
+        verts, cols, faces, ek = (_t(a, device) for a in ((r[0], r[1], r[3], r[4]) if len(r) == 5 else r))
+    faces = faces.to(torch.int64)
+    if world > 1:
+        g, allc = _gatherv([verts, cols, faces, ek], rank, world, device)
+        if rank != 0:
+            return None
+        verts, cols, faces, ek = g
+        off_f, base = 0, 0
+        for r in range(world):                                    # rebase every rank's face indices by its vertex offset
+            nf, nv = int(allc[r][2]), int(allc[r][0])
+            faces[off_f:off_f + nf] += base
+            off_f += nf
+            base += nv
+    out = merge_mesh_tensors(verts, cols, faces, ek)
+    return tuple(x.cpu().numpy() for x in out) if as_numpy else out
 
 
 # ---------------------------------------------------------------------------------------------
@@ -208,5 +246,6 @@ def integrate_host_sharded(vol, depth, rgb, intr, extrinsics, rank, world, devic
         if k + 1 < len(plan):
             issue(k + 1)
         main.wait_event(ready)
-        vol.integrate_batch(gd[:nk], gc[:nk], intr, extrinsics[c0:c0 + nk], depth_scale, depth_trunc)   # returns when done
+        with torch.cuda.stream(main):       # integrate_batch orders the volume's own streams after torch's CURRENT stream
+            vol.integrate_batch(gd[:nk], gc[:nk], intr, extrinsics[c0:c0 + nk], depth_scale, depth_trunc)   # returns when done
         free.record(main)

@@ -16,10 +16,12 @@ class TSDFVolume:
         self.voxel_length, self.sdf_trunc, self.device = float(voxel_length), float(sdf_trunc), int(device)
         self._h = C.c_void_p()
         spec = None
+        self.n_ranks = 1
         if slab is not None:
             axis, thickness, n_ranks, rank = (int(x) for x in slab[:4])
             halo = int(slab[4]) if len(slab) > 4 else 1
             spec = C.byref(_lib.SlabSpec(axis, thickness, n_ranks, rank, halo))
+            self.n_ranks = max(1, n_ranks)
         _lib.check(_lib.lib.otslam_volume_create(self.voxel_length, self.sdf_trunc,
                                                  _lib.COLOR_RGB8 if color else _lib.COLOR_NONE, self.device, spec,
                                                  C.byref(self._h)))
@@ -80,6 +82,16 @@ class TSDFVolume:
     def set_stream(self, cuda_stream):
         _lib.check(_lib.lib.otslam_volume_set_stream(self._h, C.c_void_p(int(cuda_stream) if cuda_stream else 0)))
 
+    def wait_stream(self, cuda_stream):
+        """Order the volume's streams after everything queued so far on `cuda_stream` (a raw cudaStream_t value; 0 = the
+        legacy default stream): the contract for buffers in HBM that another stream produced."""
+        _lib.check(_lib.lib.otslam_volume_wait_stream(self._h, C.c_void_p(int(cuda_stream) if cuda_stream else 0)))
+
+    def _after_torch_stream(self, tensor):
+        """A CUDA torch tensor is about to be read by the volume's own streams: wait for torch's current stream."""
+        import torch
+        self.wait_stream(torch.cuda.current_stream(tensor.device).cuda_stream)
+
     def set_batch(self, n):
         _lib.check(_lib.lib.otslam_volume_set_batch(self._h, int(n)))
 
@@ -134,6 +146,8 @@ class TSDFVolume:
             raise RuntimeError("[ScalableTSDFVolume::Integrate] Unsupported image format.")
         k = self._intr(intr)
         e = np.ascontiguousarray(extrinsics, np.float64).reshape(n, 16)
+        if on_dev:
+            self._after_torch_stream(depth)       # frames produced on a torch stream (copy, NCCL gather, rendering)
         _lib.check(_lib.lib.otslam_volume_integrate_batch(self._h, n, _lib.ptr(depth), _lib.ptr(rgb), W, H, _lib.ptr(k),
                                                           _lib.ptr(e), float(depth_scale), float(depth_trunc),
                                                           _lib.MEM_DEVICE if on_dev else _lib.MEM_HOST))
@@ -169,9 +183,56 @@ class TSDFVolume:
         return keys, dest, planes
 
     def halo_import(self, keys, planes):
-        keys = np.ascontiguousarray(keys, np.int32)
-        planes = np.ascontiguousarray(planes, np.uint8)
+        """keys [n,4] i32 / planes [n,4096] u8: numpy arrays or (contiguous) torch tensors, host or CUDA."""
+        if isinstance(keys, np.ndarray):
+            keys = np.ascontiguousarray(keys, np.int32)
+            planes = np.ascontiguousarray(planes, np.uint8)
+        else:
+            assert keys.is_contiguous() and planes.is_contiguous() and keys.element_size() == 4 and planes.element_size() == 1
+            if keys.is_cuda:
+                self._after_torch_stream(keys)    # e.g. pieces that an NCCL recv just wrote
         _lib.check(_lib.lib.otslam_volume_halo_import(self._h, len(keys), _lib.ptr(keys), _lib.ptr(planes)))
+
+    # ---- device-resident forms for the multi-GPU exchange (slab.py): torch tensors on this volume's GPU, no host copy
+    def halo_pack_tensors(self):
+        """(keys [n,4] i32, planes [n,4096] u8, pieces per destination rank [n_ranks]) -- packed in HBM, grouped by
+        destination rank, ready for ncclSend."""
+        import torch
+        n = C.c_int64(0)
+        counts = np.zeros(self.n_ranks, np.int64)
+        _lib.check(_lib.lib.otslam_volume_halo_pack(self._h, C.byref(n), _lib.ptr(counts)))
+        dev = torch.device("cuda", self.device)
+        keys = torch.empty((n.value, 4), dtype=torch.int32, device=dev)
+        planes = torch.empty((n.value, 4096), dtype=torch.uint8, device=dev)
+        if n.value:
+            _lib.check(_lib.lib.otslam_volume_halo_fetch(self._h, _lib.ptr(keys), _lib.ptr(planes)))
+        return keys, planes, counts
+
+    def extract_point_cloud_tensors(self):
+        """extract_point_cloud() with the result as torch CUDA tensors (points, colours f64 [n,3]; edge keys i32 [n,4])."""
+        import torch
+        n = C.c_int64(0)
+        _lib.check(_lib.lib.otslam_volume_extract_points(self._h, C.byref(n)))
+        dev = torch.device("cuda", self.device)
+        pts = torch.empty((n.value, 3), dtype=torch.float64, device=dev)
+        cols = torch.empty((n.value, 3), dtype=torch.float64, device=dev)
+        ek = torch.empty((n.value, 4), dtype=torch.int32, device=dev)
+        _lib.check(_lib.lib.otslam_volume_points_copy(self._h, _lib.ptr(pts), _lib.ptr(cols), _lib.ptr(ek)))
+        return pts, cols, ek
+
+    def extract_mesh_tensors(self):
+        """extract_triangle_mesh() as torch CUDA tensors (vertices, colours f64 [nv,3]; faces i32 [nf,3]; edge keys i32 [nv,4])."""
+        import torch
+        self._detach_resident_mesh()
+        nv, nf = C.c_int64(0), C.c_int64(0)
+        _lib.check(_lib.lib.otslam_volume_extract_mesh(self._h, C.byref(nv), C.byref(nf)))
+        dev = torch.device("cuda", self.device)
+        verts = torch.empty((nv.value, 3), dtype=torch.float64, device=dev)
+        cols = torch.empty((nv.value, 3), dtype=torch.float64, device=dev)
+        faces = torch.empty((nf.value, 3), dtype=torch.int32, device=dev)
+        ek = torch.empty((nv.value, 4), dtype=torch.int32, device=dev)
+        _lib.check(_lib.lib.otslam_volume_mesh_copy(self._h, _lib.ptr(verts), _lib.ptr(cols), None, _lib.ptr(faces), _lib.ptr(ek)))
+        return verts, cols, faces, ek
 
     def extract_triangle_mesh(self, normals=True):
         self._detach_resident_mesh()

@@ -258,6 +258,17 @@ int oracle_num_threads() {
 #endif
 }
 
+// bench.py's reference arm runs under torchrun, which exports OMP_NUM_THREADS=1 to every rank: the
+// CPU baseline must use the host cores it was told to use, not the inherited setting.
+int oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
 int oracle_inverse4(const double* m, double* out) { return inverse4(m, out) ? 0 : fail("singular matrix"); }
 
 // RGBDImage.create_from_color_and_depth(depth_scale, depth_trunc,

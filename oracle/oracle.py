@@ -54,6 +54,11 @@ def num_threads():
     return int(lib().oracle_num_threads())
 
 
+def set_num_threads(n):
+    """Use n OpenMP threads from now on (ignores an inherited OMP_NUM_THREADS); returns the count in effect."""
+    return int(lib().oracle_set_num_threads(int(n)))
+
+
 def inverse4(m):
     m = np.ascontiguousarray(m, np.float64)
     out = np.empty((4, 4), np.float64)
