@@ -114,3 +114,25 @@ def test_shard_plan_covers_every_frame_once_in_order():
                 lo, hi = min(c0 + r * per, c0 + nk), min(c0 + (r + 1) * per, c0 + nk)
                 seen += list(range(lo, hi))
         assert seen == list(range(n))
+
+
+def test_rank_shards_hold_exactly_the_frames_a_rank_uploads():
+    """slab.rank_shards packs, per rank, the frames integrate_host_sharded(shards=True) reads, in the order it reads them."""
+    import torch
+    from otslam_b200 import slab
+    for n, world, chunk in ((37, 4, 16), (100, 8, 32), (5, 2, 256)):
+        depth = torch.arange(n, dtype=torch.int16).view(n, 1, 1).repeat(1, 2, 3)
+        rgb = torch.arange(n, dtype=torch.uint8).view(n, 1, 1, 1).repeat(1, 2, 3, 3)
+        seen = {}
+        for r in range(world):
+            hd, hc = slab.rank_shards(depth, rgb, r, world, chunk, pin=False)
+            assert hd.shape[1:] == depth.shape[1:] and hc.shape[1:] == rgb.shape[1:] and (hc[:, 0, 0, 0] == hd[:, 0, 0].to(torch.uint8)).all()
+            off = 0
+            for c0, nk, per in slab.shard_plan(n, world, chunk):
+                lo, hi = min(c0 + r * per, c0 + nk), min(c0 + (r + 1) * per, c0 + nk)
+                assert hd[off:off + hi - lo, 0, 0].tolist() == list(range(lo, hi))
+                for f in range(lo, hi):
+                    seen[f] = r
+                off += hi - lo
+            assert off == len(hd)
+        assert sorted(seen) == list(range(n))
