@@ -82,12 +82,14 @@ __host__ __device__ inline uint32_t hash_key(uint64_t k) {
 // Voxel record: 16 bytes = ONE 128-bit transaction per voxel.
 //   .x            tsdf, f32 running mean exactly as the reference computes it
 //   .y/.z/.w      low 24 bits: integer sums of the R / G / B samples (exact; colour = sum / weight)
-//                 high 8 bits: bytes 0 / 1 / 2 of the 24-bit integration count (weight)
+//   .y/.z         high 8 bits: low / high byte of the 16-bit integration count (weight); .w's high byte is 0
 // Exact integer colour sums stay within 24 bits for <= 65535 integrations of a voxel
-// (255 * 65535 < 2^24); the host refuses more frames per volume (OTSLAM_ERR_OVERFLOW).
-// All-zero bits == the reference's freshly opened voxel (tsdf 0, weight 0, colour 0).
+// (255 * 65535 < 2^24), which is also what the 16-bit count holds; the host refuses more frames per
+// volume (OTSLAM_ERR_OVERFLOW).  All-zero bits == the reference's freshly opened voxel (tsdf 0, weight 0,
+// colour 0).  (Round 1 spread a 24-bit count over all three words: two more shifts / masks per update and a
+// second carry level for a range the frame limit never reaches.)
 __host__ __device__ inline uint32_t rec_weight(const uint4& r) {
-    return (r.y >> 24) | ((r.z >> 24) << 8) | ((r.w >> 24) << 16);
+    return (r.y >> 24) | ((r.z >> 24) << 8);
 }
 __host__ __device__ inline uint4 rec_pack(float tsdf, uint32_t w, uint32_t rs, uint32_t gs, uint32_t bs) {
     uint4 r;
@@ -98,7 +100,7 @@ __host__ __device__ inline uint4 rec_pack(float tsdf, uint32_t w, uint32_t rs, u
 #endif
     r.y = rs | ((w & 0xFFu) << 24);
     r.z = gs | (((w >> 8) & 0xFFu) << 24);
-    r.w = bs | (((w >> 16) & 0xFFu) << 24);
+    r.w = bs;
     return r;
 }
 constexpr int kMaxFramesPerVolume = 65535;

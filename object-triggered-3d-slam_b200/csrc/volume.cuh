@@ -75,7 +75,7 @@ struct otslam_volume {
     uint16_t* d_raw_depth[otslam::kNB] = {};
     uint8_t* d_raw_rgb[otslam::kNB] = {};
     uint2* d_packed[otslam::kNB] = {};
-    size_t raw_frames_cap = 0, raw_px_cap = 0, packed_cap = 0;
+    size_t raw_frames_cap = 0, raw_px_cap = 0, packed_cap = 0, packed_px = 0;
     size_t raw_depth_bytes_per_px = 2;
     cudaEvent_t ev_copied[otslam::kNB] = {}, ev_raw_free[otslam::kNB] = {};
     otslam::FrameDev* d_frames[otslam::kNB] = {};
