@@ -34,3 +34,37 @@ T_fix = np.array([[0, -1, 0, 0], [0, 0, -1, 0], [1, 0, 0, 0], [0, 0, 0, 1]])
 VOXEL_LENGTH = env_float("OTSLAM_VOXEL_LENGTH", 0.01)      # reference: voxel_length=0.01
 SDF_TRUNC = env_float("OTSLAM_SDF_TRUNC", 0.04)            # reference: sdf_trunc=0.04
 DEPTH_SCALE, DEPTH_TRUNC = 1000.0, 3.0
+
+
+# ---- shared tail of the two filter scripts (reference reconstruct_rgbd_filter.py:112-140 ==
+#      multi_reconstruct_rgbd_filter.py:110-137): lives here so that neither script has to import the other
+#      (importing reconstruct_rgbd_filter would run ITS module-level directory set-up for a different dataset)
+Z_FILTER_THRESHOLD = 0.03          # removes floor points (reference :22)
+NUMBER_OF_POINTS = 100000          # reference :123
+POST_VOXEL = float(os.environ.get("OTSLAM_POST_VOXEL", "0") or 0)
+POST_SOR = os.environ.get("OTSLAM_POST_SOR", "")
+SAMPLE_SEED = os.environ.get("OTSLAM_SAMPLE_SEED")
+
+
+def filter_and_save(mesh, obj_name, save_dir):
+    if len(mesh.vertices) == 0:
+        print("❌ Warning: Mesh is empty! Check poses or depth scale.")
+        return None
+    print(f"   Filtering points below Z < {Z_FILTER_THRESHOLD:.2f}m...")
+    seed = None if SAMPLE_SEED is None else int(SAMPLE_SEED)
+    pcd = mesh.sample_points_uniformly(number_of_points=NUMBER_OF_POINTS, seed=seed)
+    points, colors = np.asarray(pcd.points), np.asarray(pcd.colors)
+    mask = points[:, 2] >= Z_FILTER_THRESHOLD
+    filtered_pcd = o3d.geometry.PointCloud()
+    filtered_pcd.points = o3d.utility.Vector3dVector(points[mask])
+    filtered_pcd.colors = o3d.utility.Vector3dVector(colors[mask])
+    if POST_VOXEL > 0:                                     # north_star stage, off by default (the reference does not run it)
+        filtered_pcd = filtered_pcd.voxel_down_sample(POST_VOXEL)
+    if POST_SOR:
+        k, ratio = POST_SOR.split(",")
+        filtered_pcd, _ = filtered_pcd.remove_statistical_outlier(int(k), float(ratio))
+    print(f"   Points remaining: {len(filtered_pcd.points)}")
+    output_path = os.path.join(save_dir, f"{obj_name}.ply")
+    o3d.io.write_point_cloud(output_path, filtered_pcd)
+    print(f"✅ Saved 3D Model: {output_path}")
+    return output_path

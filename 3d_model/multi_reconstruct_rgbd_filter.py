@@ -22,10 +22,9 @@ if os.environ.get("OTSLAM_OBJECT_RANGES"):
 
 intrinsics = o3d.camera.PinholeCameraIntrinsic(width, height, fx, fy, cx, cy)
 
-import reconstruct_rgbd_filter as _filter  # noqa: E402  (shared sampling / z-filter / save tail)
+import _common  # noqa: E402  (shared sampling / z-filter / save tail)
 
-_filter.save_dir = save_dir
-Z_FILTER_THRESHOLD = _filter.Z_FILTER_THRESHOLD
+Z_FILTER_THRESHOLD = _common.Z_FILTER_THRESHOLD
 
 
 def _range_triples(start_frame, end_frame):
@@ -52,7 +51,7 @@ def _finish(obj_name, volume, frames_processed):
     print("\n   Extracting mesh...")
     mesh = volume.extract_triangle_mesh()
     mesh.compute_vertex_normals()
-    _filter.filter_and_save(mesh, obj_name)
+    _common.filter_and_save(mesh, obj_name, save_dir)
 
 
 def reconstruct_range(obj_name, start_frame, end_frame):

@@ -7,20 +7,14 @@ removal on the filtered cloud."""
 import glob
 import os
 
-import numpy as np
-
+import _common
+from _common import (Z_FILTER_THRESHOLD, NUMBER_OF_POINTS)  # noqa: F401  (the reference's module constants)
 from _common import (DEPTH_SCALE, DEPTH_TRUNC, SDF_TRUNC, T_fix, VOXEL_LENGTH, cx, cy, fx, fy, height, o3d, scan_dirs,
                      width)
 from otslam_b200 import pipeline
 
 base_dir, _d = scan_dirs("/home/ros2_env/taki/otslam/3d_model/object_scan_2")
 color_dir, depth_dir, pose_dir, save_dir = _d["color_dir"], _d["depth_dir"], _d["pose_dir"], _d["save_dir"]
-
-Z_FILTER_THRESHOLD = 0.03          # removes floor points (reference :22)
-NUMBER_OF_POINTS = 100000          # reference :123
-POST_VOXEL = float(os.environ.get("OTSLAM_POST_VOXEL", "0") or 0)
-POST_SOR = os.environ.get("OTSLAM_POST_SOR", "")
-SAMPLE_SEED = os.environ.get("OTSLAM_SAMPLE_SEED")
 
 intrinsics = o3d.camera.PinholeCameraIntrinsic(width, height, fx, fy, cx, cy)
 
@@ -35,28 +29,8 @@ def get_unique_object_names():
 
 
 def filter_and_save(mesh, obj_name):
-    """Shared tail of the two filter scripts (reference :112-140)."""
-    if len(mesh.vertices) == 0:
-        print("❌ Warning: Mesh is empty! Check poses or depth scale.")
-        return None
-    print(f"   Filtering points below Z < {Z_FILTER_THRESHOLD:.2f}m...")
-    seed = None if SAMPLE_SEED is None else int(SAMPLE_SEED)
-    pcd = mesh.sample_points_uniformly(number_of_points=NUMBER_OF_POINTS, seed=seed)
-    points, colors = np.asarray(pcd.points), np.asarray(pcd.colors)
-    mask = points[:, 2] >= Z_FILTER_THRESHOLD
-    filtered_pcd = o3d.geometry.PointCloud()
-    filtered_pcd.points = o3d.utility.Vector3dVector(points[mask])
-    filtered_pcd.colors = o3d.utility.Vector3dVector(colors[mask])
-    if POST_VOXEL > 0:
-        filtered_pcd = filtered_pcd.voxel_down_sample(POST_VOXEL)
-    if POST_SOR:
-        k, ratio = POST_SOR.split(",")
-        filtered_pcd, _ = filtered_pcd.remove_statistical_outlier(int(k), float(ratio))
-    print(f"   Points remaining: {len(filtered_pcd.points)}")
-    output_path = os.path.join(save_dir, f"{obj_name}.ply")
-    o3d.io.write_point_cloud(output_path, filtered_pcd)
-    print(f"✅ Saved 3D Model: {output_path}")
-    return output_path
+    """Tail of reconstruct_object (reference :112-140); shared with the multi-range script through _common."""
+    return _common.filter_and_save(mesh, obj_name, save_dir)
 
 
 def reconstruct_object(obj_name):

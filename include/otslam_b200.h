@@ -87,8 +87,8 @@ int otslam_volume_wait_stream(otslam_volume* v, void* producer_stream);
 /* frames fused per block residency in integrate_batch (1..32, default 32) */
 int otslam_volume_set_batch(otslam_volume* v, int frames_per_batch);
 
-/* CTAs per block along z in the integration kernel: 0 = automatic (2 when a batch touches fewer
- * than 800 blocks, else 1), 1, 2 or 4; results are bit-identical for every setting */
+/* CTAs per block along z in the integration kernel: 0 = automatic (2, or 4 / 8 when a batch touches fewer
+ * than 1184 / 592 blocks), 1, 2, 4 or 8; results are bit-identical for every setting */
 int otslam_volume_set_zsplit(otslam_volume* v, int zsplit);
 
 /* kernel timing with CUDA events on the volume's stream (bench.py roofline): enable > 0 switches

@@ -13,6 +13,33 @@ import numpy as np
 
 MAX_DEPTH_M = 5.0          # scanner_node.cpp:278
 
+# File-name patterns of the reference's capture tools: (color, depth, pose) templates over (label, count).
+#   scanner       ScannerNode::save_files, scanner_node.cpp:268-299        <label>_<n>.{jpg,png,txt}
+#   center_table  rgbd_capture_node_2.cpp:168-171 (manual SPACE capture)    center_table_color_0007.jpg ...
+#   gt            rgbd_capture_node_gt.cpp:126-128 (ground-truth odometry)  gt_color_0007.png (PNG colour) ...
+#   plain         _rgbd_capture_node.cpp:104-110 (older tool)               color_0007.png ...
+PATTERNS = {
+    "scanner": ("{label}_{n}.jpg", "{label}_{n}.png", "{label}_{n}.txt"),
+    "center_table": ("center_table_color_{n:04d}.jpg", "center_table_depth_{n:04d}.png", "center_table_pose_{n:04d}.txt"),
+    "gt": ("gt_color_{n:04d}.png", "gt_depth_{n:04d}.png", "gt_pose_{n:04d}.txt"),
+    "plain": ("color_{n:04d}.png", "depth_{n:04d}.png", "pose_{n:04d}.txt"),
+}
+
+
+def pose_from_quaternion(qx, qy, qz, qw, tx, ty, tz):
+    """4x4 pose from a TF / odometry message as the capture tools build it: tf2::Matrix3x3(q) (setRotation: s = 2 / |q|^2,
+    products in tf2's order) + translation (rgbd_capture_node_2.cpp:199-221, rgbd_capture_node_gt.cpp:148-168)."""
+    d = qx * qx + qy * qy + qz * qz + qw * qw
+    s = 2.0 / d
+    xs, ys, zs = qx * s, qy * s, qz * s
+    wx, wy, wz = qw * xs, qw * ys, qw * zs
+    xx, xy, xz = qx * xs, qx * ys, qx * zs
+    yy, yz, zz = qy * ys, qy * zs, qz * zs
+    return np.array([[1.0 - (yy + zz), xy - wz, xz + wy, tx],
+                     [xy + wz, 1.0 - (xx + zz), yz - wx, ty],
+                     [xz - wy, yz + wx, 1.0 - (xx + yy), tz],
+                     [0.0, 0.0, 0.0, 1.0]])
+
 
 def depth_to_u16_mm(depth_m):
     """float32 metres -> uint16 millimetres exactly as scanner_node.cpp:277-281 does."""
@@ -29,17 +56,19 @@ def pose_text(T):
     return "".join(" ".join("%.6f" % v for v in T[r]) + "\n" for r in range(4))
 
 
-def save_frame(base_dir, label, count, rgb_u8, depth_m_or_u16, pose_body_to_map):
-    """Write one scan as <label>_<count>.{jpg,png,txt}; depth may be float metres or ready u16 mm."""
+def save_frame(base_dir, label, count, rgb_u8, depth_m_or_u16, pose_body_to_map, pattern="scanner"):
+    """Write one scan in the layout of one of the reference's capture tools (PATTERNS; default: the scanner action
+    server's <label>_<count>.{jpg,png,txt}); depth may be float metres or ready u16 mm.  Returns the three paths' stem
+    for the scanner pattern, else the tuple of file names."""
     import cv2
     for sub in ("color", "depth", "poses"):
         os.makedirs(os.path.join(base_dir, sub), exist_ok=True)
     depth = np.asarray(depth_m_or_u16)
     if depth.dtype != np.uint16:
         depth = depth_to_u16_mm(depth)
-    stem = f"{label}_{count}"
-    cv2.imwrite(os.path.join(base_dir, "color", stem + ".jpg"), np.ascontiguousarray(np.asarray(rgb_u8)[..., ::-1]))
-    cv2.imwrite(os.path.join(base_dir, "depth", stem + ".png"), depth)
-    with open(os.path.join(base_dir, "poses", stem + ".txt"), "w") as f:
+    names = tuple(t.format(label=label, n=count) for t in PATTERNS[pattern])
+    cv2.imwrite(os.path.join(base_dir, "color", names[0]), np.ascontiguousarray(np.asarray(rgb_u8)[..., ::-1]))
+    cv2.imwrite(os.path.join(base_dir, "depth", names[1]), depth)
+    with open(os.path.join(base_dir, "poses", names[2]), "w") as f:
         f.write(pose_text(pose_body_to_map))
-    return stem
+    return f"{label}_{count}" if pattern == "scanner" else names

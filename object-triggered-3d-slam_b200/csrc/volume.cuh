@@ -60,6 +60,7 @@ struct otslam_volume {
     uint32_t* d_masks[otslam::kNB] = {};   // entry -> bit f set when frame f of the batch touches it
     int32_t* d_list[otslam::kNB] = {};     // entries touched by the batch (each once)
     int32_t* d_order[otslam::kNB] = {};    // the same entries, most-frames-first (launch order of the integration CTAs)
+    uint32_t* d_lmask[otslam::kNB] = {};   // their frame masks in that order (the hash-side masks are cleared when this is built)
 
     // block pool: chunks of kChunkBlocks blocks, 64 KiB per block
     std::vector<uint4*> chunks;

@@ -32,10 +32,12 @@ def _header(kind_lines):
 
 def write_point_cloud(filename, pointcloud, write_ascii=False, compressed=False, print_progress=False):
     """o3d.io.write_point_cloud (reconstruct_rgbd_filter.py:140, fusion/hybrid_map.py:121)."""
+    if str(filename).lower().endswith(".pcd"):
+        return _write_pcd(filename, pointcloud, write_ascii)
     if write_ascii:
         raise RuntimeError("ASCII PLY output is not supported (the reference writes binary)")
     if not str(filename).lower().endswith(".ply"):
-        raise RuntimeError("Write geometry::PointCloud failed: unknown file extension (only .ply is produced by the reference)")
+        raise RuntimeError("Write geometry::PointCloud failed: unknown file extension (.ply and .pcd are supported)")
     p = pointcloud.points
     n = len(p)
     if n == 0:
@@ -61,6 +63,84 @@ def write_point_cloud(filename, pointcloud, write_ascii=False, compressed=False,
         f.write(_header(lines))
         f.write(rec.tobytes())
     return True
+
+
+def _write_pcd(filename, pointcloud, write_ascii=False):
+    """PCD v0.7 as Open3D's WritePointCloudToPCD lays it out (north_star names .pcd beside .ply; the reference itself
+    only writes .ply): float32 x y z, optional float32 normal_x normal_y normal_z, optional `rgb` = one float32 whose BITS
+    are r << 16 | g << 8 | b, DATA binary (or ascii with write_ascii=True, rgb printed as the same float)."""
+    p = np.asarray(pointcloud.points, np.float64)
+    n = len(p)
+    if n == 0:
+        print("[Open3D WARNING] Write PCD failed: point cloud has 0 points.")
+        return False
+    fields, dt = ["x", "y", "z"], [("p", "<f4", 3)]
+    if pointcloud.has_normals():
+        fields += ["normal_x", "normal_y", "normal_z"]
+        dt.append(("n", "<f4", 3))
+    if pointcloud.has_colors():
+        fields.append("rgb")
+        dt.append(("c", "<u4"))
+    k = len(fields)
+    header = ("# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\n"
+              f"FIELDS {' '.join(fields)}\nSIZE {' '.join(['4'] * k)}\nTYPE {' '.join(['F'] * k)}\nCOUNT {' '.join(['1'] * k)}\n"
+              f"WIDTH {n}\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS {n}\nDATA {'ascii' if write_ascii else 'binary'}\n")
+    rec = np.empty(n, np.dtype(dt))
+    rec["p"] = p
+    if pointcloud.has_normals():
+        rec["n"] = pointcloud.normals
+    if pointcloud.has_colors():
+        c = _color_bytes(pointcloud.colors).astype(np.uint32)
+        rec["c"] = (c[:, 0] << 16) | (c[:, 1] << 8) | c[:, 2]
+    with open(filename, "wb") as f:
+        f.write(header.encode())
+        if write_ascii:
+            cols = [rec["p"]] + ([rec["n"]] if pointcloud.has_normals() else []) + \
+                   ([rec["c"].view(np.float32)[:, None]] if pointcloud.has_colors() else [])
+            np.savetxt(f, np.concatenate(cols, axis=1), fmt="%.10g")
+        else:
+            rec.tofile(f)
+    return True
+
+
+def _read_pcd(filename):
+    with open(filename, "rb") as f:
+        data = f.read()
+    hdr, off = {}, 0
+    while True:
+        nl = data.find(b"\n", off)
+        if nl < 0:
+            raise RuntimeError("Read PCD failed: no DATA line")
+        line = data[off:nl].decode("ascii", "replace").strip()
+        off = nl + 1
+        if not line or line.startswith("#"):
+            continue
+        t = line.split()
+        hdr[t[0].upper()] = t[1:]
+        if t[0].upper() == "DATA":
+            break
+    fields, sizes, types = hdr["FIELDS"], [int(x) for x in hdr["SIZE"]], hdr["TYPE"]
+    counts = [int(x) for x in hdr.get("COUNT", ["1"] * len(fields))]
+    n = int(hdr["POINTS"][0])
+    np_t = {("F", 4): "<f4", ("F", 8): "<f8", ("U", 1): "u1", ("U", 2): "<u2", ("U", 4): "<u4", ("I", 1): "i1", ("I", 2): "<i2", ("I", 4): "<i4"}
+    dt = np.dtype([(f, np_t[(t, s)], c) if c > 1 else (f, np_t[(t, s)]) for f, s, t, c in zip(fields, sizes, types, counts)])
+    kind = hdr["DATA"][0].lower()
+    if kind == "binary":
+        a = np.frombuffer(data, dt, n, off)
+    elif kind == "ascii":
+        tok = np.array(data[off:].split(), dtype=np.float64).reshape(n, -1)
+        a = np.empty(n, dt)
+        for i, f in enumerate(fields):
+            a[f] = tok[:, i].astype(np.float32).view(np.uint32) if (f in ("rgb", "rgba") and dt[f] == np.dtype("<u4")) else tok[:, i]
+    else:
+        raise RuntimeError(f"Read PCD failed: DATA {kind} is not supported")
+    pts = np.stack([a["x"], a["y"], a["z"]], 1).astype(np.float64)
+    nrm = np.stack([a["normal_x"], a["normal_y"], a["normal_z"]], 1).astype(np.float64) if "normal_x" in fields else None
+    col = None
+    if "rgb" in fields or "rgba" in fields:
+        bits = np.ascontiguousarray(a["rgb" if "rgb" in fields else "rgba"]).view(np.uint32)
+        col = np.stack([(bits >> 16) & 255, (bits >> 8) & 255, bits & 255], 1).astype(np.float64) / 255.0
+    return pts, nrm, col
 
 
 def _color_bytes(c):
@@ -212,9 +292,9 @@ def read_point_cloud(filename, format="auto", remove_nan_points=False, remove_in
     give an empty cloud plus a warning."""
     pc = geometry.PointCloud()
     try:
-        pts, nrm, col = _vertex_arrays(_read_ply(filename))
+        pts, nrm, col = _read_pcd(filename) if str(filename).lower().endswith(".pcd") else _vertex_arrays(_read_ply(filename))
     except Exception as e:  # noqa: BLE001
-        print(f"[Open3D WARNING] Read PLY failed: {e}")
+        print(f"[Open3D WARNING] Read {'PCD' if str(filename).lower().endswith('.pcd') else 'PLY'} failed: {e}")
         return pc
     pc.points = pts
     if nrm is not None:

@@ -38,7 +38,7 @@ def assert_parity(gv, ov, color=True):
 
 
 @pytest.mark.parametrize("vl", [0.01, 0.005])
-@pytest.mark.parametrize("mode", ["per_frame", "batch_host", "batch_device", "batch_of_1", "batch_of_5", "zsplit_1", "zsplit_2", "zsplit_4"])
+@pytest.mark.parametrize("mode", ["per_frame", "batch_host", "batch_device", "batch_of_1", "batch_of_5", "zsplit_1", "zsplit_2", "zsplit_4", "zsplit_8"])
 def test_integration_parity(table_seq, vl, mode):
     from otslam_b200.volume import TSDFVolume
     seq, d, c = table_seq

@@ -158,3 +158,49 @@ def test_multi_objects_in_parallel_match_sequential(capture):
     assert "frames integrated" in out
     for k in ranges:
         assert open(os.path.join(base, "3d_reconst", f"{k}.ply"), "rb").read() == seq_out[k]
+
+
+def test_reconstruct_rgbd_gt_script(tmp_path):
+    """reconstruct_rgbd_gt.py on a tree written the way rgbd_capture_node_gt.cpp writes it (gt_color_0000.png,
+    gt_depth_0000.png, gt_pose_0000.txt; poses are camera BODY -> map, the script's own T_fix = standard body -> optical)."""
+    import otslam_b200.o3d_compat as o3d
+    from otslam_b200 import capture, synth
+    T_fix_gt = np.array([[0, 0, 1, 0], [-1, 0, 0, 0], [0, -1, 0, 0], [0, 0, 0, 1]], np.float64)
+    base = str(tmp_path)
+    poses = synth.trajectory("table", 24)[::4]
+    seq = synth.make_sequence("table", 24, poses=poses)
+    d, c = seq.numpy()
+    pose_body = [np.round(T @ np.linalg.inv(T_fix_gt), 6) for T in poses]
+    ext = []
+    for k in range(len(poses)):
+        capture.save_frame(base, "gt", k, c[k], d[k], pose_body[k], pattern="gt")
+        ext.append(np.linalg.inv(np.loadtxt(os.path.join(base, "poses", f"gt_pose_{k:04d}.txt")) @ T_fix_gt))
+    out = run_script("3d_model/reconstruct_rgbd_gt.py", {"OTSLAM_BASE_DIR": base})
+    assert f"Found {len(poses)} frames" in out and "Success! Saved to" in out
+    m = o3d.io.read_triangle_mesh(os.path.join(base, "3d_reconst", "object_reconst_gt.ply"))
+    ov = oracle.Volume(0.01, 0.04)
+    for k in range(len(poses)):                                     # colour PNGs are lossless: the oracle sees the same pixels
+        ov.integrate(oracle.depth_convert(d[k]), c[k], seq.fxfycxcy, ext[k])
+    verts, cols, faces, ek = ov.extract_triangle_mesh()
+    assert len(verts) > 1000 and len(m.vertices) == len(verts) and len(m.triangles) == len(faces) and m.has_vertex_normals()
+    assert cKDTree(verts).query(m.vertices)[0].max() == 0.0
+
+
+def test_check_one_frame_script(tmp_path):
+    """check_one_frame.py -- the reference's only call site of create_from_rgbd_image + voxel_down_sample
+    (check_one_frame.py:27-28), on color_0000.png / depth_0000.png as _rgbd_capture_node.cpp names them."""
+    import otslam_b200.o3d_compat as o3d
+    from otslam_b200 import capture, synth
+    base = str(tmp_path)
+    seq = synth.make_sequence("chair_table", 40, subsample=(5, 40))
+    d, c = seq.numpy()
+    capture.save_frame(base, "x", 0, c[0], d[0], np.eye(4), pattern="plain")
+    out = run_script("3d_model/check_one_frame.py", {"OTSLAM_BASE_DIR": base})
+    assert "Displayed single-frame point cloud" in out
+    got = o3d.io.read_point_cloud(os.path.join(base, "one_frame_cloud.ply"))
+    pts, cols = oracle.backproject_rgbd(oracle.depth_convert(d[0], 1000.0, 5.0), c[0], seq.fxfycxcy)
+    ep, ec, _, _ = oracle.voxel_down_sample(pts, cols, 0.01)
+    assert len(got.points) == len(ep) > 1000
+    o1, o2 = np.lexsort(got.points.T[::-1]), np.lexsort(ep.T[::-1])
+    assert (got.points[o1] == ep[o2]).all()
+    assert np.abs(got.colors[o1] - ec[o2]).max() <= 0.5 / 255 + 1e-9

@@ -241,3 +241,54 @@ def test_capture_depth_conversion_matches_scanner_node():
     assert out[0].tolist() == exp
     assert out[0, 0] == 0 and out[0, 6] == 5000 and out[0, 7] == 5000 and out[0, 8] == 0 and out[0, 9] == 0 and out[0, 4] == 2
     assert capture.pose_text(np.eye(4)).splitlines()[3] == "0.000000 0.000000 0.000000 1.000000"
+
+
+def test_pcd_layout_and_round_trip(tmp_path):
+    """north_star names .pcd beside .ply: PCD v0.7 in Open3D's layout (float32 xyz, rgb = float whose bits are r<<16|g<<8|b)."""
+    rng = np.random.default_rng(3)
+    pc = o3d.geometry.PointCloud()
+    pc.points = rng.random((7, 3)); pc.colors = rng.random((7, 3))
+    p = str(tmp_path / "c.pcd")
+    assert o3d.io.write_point_cloud(p, pc)
+    raw = open(p, "rb").read()
+    hdr, body = raw[:raw.index(b"DATA binary\n") + 12], raw[raw.index(b"DATA binary\n") + 12:]
+    assert hdr.decode().splitlines()[:4] == ["# .PCD v0.7 - Point Cloud Data file format", "VERSION 0.7", "FIELDS x y z rgb", "SIZE 4 4 4 4"]
+    assert b"TYPE F F F F\nCOUNT 1 1 1 1\nWIDTH 7\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS 7\n" in hdr and len(body) == 7 * 16
+    rec = np.frombuffer(body, np.dtype([("p", "<f4", 3), ("c", "<u4")]))
+    assert (rec["p"] == pc.points.astype(np.float32)).all()
+    cb = np.floor(pc.colors * 255.0 + 0.5).astype(np.uint32)
+    assert (rec["c"] == ((cb[:, 0] << 16) | (cb[:, 1] << 8) | cb[:, 2])).all()
+    q = o3d.io.read_point_cloud(p)
+    assert (q.points == pc.points.astype(np.float32).astype(np.float64)).all() and np.abs(q.colors - pc.colors).max() <= 0.5 / 255 + 1e-12
+    pc.normals = rng.random((7, 3))
+    pa = str(tmp_path / "a.pcd")
+    assert o3d.io.write_point_cloud(pa, pc, write_ascii=True)
+    qa = o3d.io.read_point_cloud(pa)
+    assert qa.has_normals() and np.abs(qa.points - pc.points).max() < 1e-6 and np.abs(qa.colors - pc.colors).max() <= 0.5 / 255 + 1e-12
+    assert not o3d.io.write_point_cloud(str(tmp_path / "e.pcd"), o3d.geometry.PointCloud())
+
+
+def test_capture_tool_name_patterns_and_tf_pose(tmp_path):
+    """The manual capture tools' layouts (rgbd_capture_node_2.cpp:168-171, rgbd_capture_node_gt.cpp:126-128,
+    _rgbd_capture_node.cpp:104-110) and their quaternion -> 4x4 pose."""
+    from otslam_b200 import capture
+    rgb = np.zeros((4, 6, 3), np.uint8); rgb[..., 0] = 200
+    depth = np.full((4, 6), 1.5, np.float32)
+    T = capture.pose_from_quaternion(0.0, 0.0, np.sin(0.25), np.cos(0.25), 1.0, 2.0, 0.5)      # yaw 0.5 rad
+    assert np.allclose(T[:3, :3], [[np.cos(0.5), -np.sin(0.5), 0], [np.sin(0.5), np.cos(0.5), 0], [0, 0, 1]], atol=1e-15)
+    assert np.allclose(T[:3, :3] @ T[:3, :3].T, np.eye(3), atol=1e-15) and T[:, 3].tolist() == [1.0, 2.0, 0.5, 1.0]
+    want = {"center_table": ("center_table_color_0007.jpg", "center_table_depth_0007.png", "center_table_pose_0007.txt"),
+            "gt": ("gt_color_0007.png", "gt_depth_0007.png", "gt_pose_0007.txt"),
+            "plain": ("color_0007.png", "depth_0007.png", "pose_0007.txt")}
+    import cv2
+    for pat, names in want.items():
+        base = str(tmp_path / pat)
+        assert capture.save_frame(base, "ignored", 7, rgb, depth, T, pattern=pat) == names
+        for sub, nm in zip(("color", "depth", "poses"), names):
+            assert os.path.exists(os.path.join(base, sub, nm))
+        d = cv2.imread(os.path.join(base, "depth", names[1]), cv2.IMREAD_UNCHANGED)
+        assert d.dtype == np.uint16 and (d == 1500).all()
+        assert np.allclose(np.loadtxt(os.path.join(base, "poses", names[2])), T, atol=5e-7)
+    c = cv2.imread(os.path.join(str(tmp_path / "gt"), "color", "gt_color_0007.png"), cv2.IMREAD_UNCHANGED)
+    assert (c[..., ::-1] == rgb).all()                     # PNG colour is lossless
+    assert capture.save_frame(str(tmp_path / "s"), "Object_3", 12, rgb, depth, T) == "Object_3_12"
