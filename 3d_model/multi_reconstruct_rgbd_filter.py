@@ -68,17 +68,23 @@ def reconstruct_range(obj_name, start_frame, end_frame):
 
 def main():
     print(f"Starting reconstruction for {len(OBJECT_RANGES)} objects...")
-    if os.environ.get("OTSLAM_PARALLEL_OBJECTS", "0") not in ("", "0"):
-        # config 3: every object is an independent volume -> integrate them concurrently on the GPU
+    if os.environ.get("OTSLAM_PARALLEL_OBJECTS", "1") not in ("", "0") and 1 < len(OBJECT_RANGES) <= 8:
+        # config 3: every object is an independent volume -> their frame loops go through ONE multi-object arena (one work
+        # list and one integration launch per batch over the union of the objects' blocks); results per object are
+        # bit-identical to the sequential loop below (OTSLAM_PARALLEL_OBJECTS=0), only the order of the messages differs
         jobs, names = [], []
         for name, (start, end) in OBJECT_RANGES.items():
+            print("\n========================================")
+            print(f"🛠️  Processing: {name} (Frames {start} -> {end})")
+            print("========================================")
             jobs.append((_new_volume(), _range_triples(start, end),
                          dict(intrinsics=intrinsics, T_fix=T_fix, depth_scale=DEPTH_SCALE, depth_trunc=DEPTH_TRUNC, skip_errors=True,
+                              progress=lambda label, i, n: print(f"\r   Integrate: Frame {label}", end="", flush=True),
                               on_error=lambda label, e: print(f"\n   ⚠️ Error on frame {label}: {e}"))))
             names.append(name)
         counts = pipeline.integrate_many(jobs)
         for name, (vol, _, _), n in zip(names, jobs, counts):
-            print(f"\n🛠️  Processing: {name} ({n} frames integrated)")
+            print(f"\n🛠️  {name}: {n} frames integrated")
             _finish(name, vol, n)
     else:
         for name, (start, end) in OBJECT_RANGES.items():

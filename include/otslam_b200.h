@@ -87,8 +87,8 @@ int otslam_volume_wait_stream(otslam_volume* v, void* producer_stream);
 /* frames fused per block residency in integrate_batch (1..32, default 32) */
 int otslam_volume_set_batch(otslam_volume* v, int frames_per_batch);
 
-/* CTAs per block along z in the integration kernel: 0 = automatic (2, or 4 / 8 when a batch touches fewer
- * than 1184 / 592 blocks), 1, 2, 4 or 8; results are bit-identical for every setting */
+/* CTAs per block along z in the integration kernel: 0 = default (2), 1, 2, 4 or 8; results are bit-identical for
+ * every setting */
 int otslam_volume_set_zsplit(otslam_volume* v, int zsplit);
 
 /* kernel timing with CUDA events on the volume's stream (bench.py roofline): enable > 0 switches
@@ -114,6 +114,20 @@ int otslam_volume_integrate_f32(otslam_volume* v, const float* depth_m, const ui
 int otslam_volume_integrate_batch(otslam_volume* v, int n_frames, const uint16_t* depth, const uint8_t* rgb,
                                   int width, int height, const double intr[4], const double* extrinsics,
                                   double depth_scale, double depth_trunc, int memory);
+
+/* ---- multi-object arenas: BASELINE configs[2] = 3d_model/multi_reconstruct_rgbd_filter.py:139-145 (several objects, each its
+ *      own ScalableTSDFVolume, reconstructed one after the other).  An arena holds up to 8 such volumes in ONE block hash /
+ *      pool with the object id folded into the block key, so that a batch of frames drawn from several objects is one work
+ *      list and one integration launch over the union of their touched blocks (small per-object volumes cannot fill 148 SMs
+ *      on their own).  set_objects on an empty, un-sharded volume; object_ids [n_frames] says which object each frame
+ *      belongs to (frame order is preserved per object, which is all the running means depend on); select_object chooses
+ *      the object that extract_mesh / extract_points / export_blocks / num_blocks / stats address.  Every object's result
+ *      is bit-identical to integrating its frames into a volume of its own.  |block x key| < 2^17 inside an arena. */
+int otslam_volume_set_objects(otslam_volume* v, int n_objects);
+int otslam_volume_select_object(otslam_volume* v, int object_id);
+int otslam_volume_integrate_batch_objects(otslam_volume* v, int n_frames, const uint16_t* depth, const uint8_t* rgb,
+                                          int width, int height, const double intr[4], const double* extrinsics,
+                                          const int32_t* object_ids, double depth_scale, double depth_trunc, int memory);
 
 /* ---- inspection / checkpoint (parity dumps) */
 int otslam_volume_num_blocks(otslam_volume* v, int64_t* n_blocks);

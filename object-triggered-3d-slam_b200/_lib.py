@@ -49,6 +49,9 @@ _SIGS = {
     "otslam_volume_integrate_u16": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _d, _d]),
     "otslam_volume_integrate_f32": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
     "otslam_volume_integrate_batch": (_i, [_vp, _i, _vp, _vp, _i, _i, _vp, _vp, _d, _d, _i]),
+    "otslam_volume_set_objects": (_i, [_vp, _i]),
+    "otslam_volume_select_object": (_i, [_vp, _i]),
+    "otslam_volume_integrate_batch_objects": (_i, [_vp, _i, _vp, _vp, _i, _i, _vp, _vp, _vp, _d, _d, _i]),
     "otslam_volume_num_blocks": (_i, [_vp, C.POINTER(_i64)]),
     "otslam_volume_export_blocks": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "otslam_volume_stats": (_i, [_vp, C.POINTER(_i64), C.POINTER(_u64), C.POINTER(_u64)]),

@@ -78,6 +78,17 @@ __host__ __device__ inline uint32_t hash_key(uint64_t k) {
     return (uint32_t)k;
 }
 
+// ---- multi-object arenas (config 3: multi_reconstruct_rgbd_filter.py, several objects, each "its own volume"): the
+// objects share ONE block hash / pool / per-batch work list, so that one integration launch covers the union of their
+// touched blocks.  The object id lives in the block key: object o (0..7) owns the x-key window
+// [o * 2^18 - 2^20 + 0, +2^18), i.e. its true block coordinate kx in [-2^17, 2^17) is stored as kx + obj_key_offset(o).
+// Blocks of different objects are never neighbours, and sorting by key groups the blocks by object.
+constexpr int kObjShift = 18;
+constexpr int kMaxObjects = 8;
+constexpr int kObjHalf = 1 << (kObjShift - 1);            // |true kx| limit inside an arena
+__host__ __device__ inline int obj_key_offset(int o) { return (o << kObjShift) + kObjHalf - kKeyBias; }
+__host__ __device__ inline int obj_of_key_x(int kx_stored) { return (kx_stored + kKeyBias) >> kObjShift; }
+
 // ---------------------------------------------------------------------------------------------
 // Voxel record: 16 bytes = ONE 128-bit transaction per voxel.
 //   .x            tsdf, f32 running mean exactly as the reference computes it

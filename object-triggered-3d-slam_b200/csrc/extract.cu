@@ -58,6 +58,7 @@ struct ExtractCtx {
     int n;
     SlabSpec slab;
     double vl, half;
+    int x_off;                // multi-object arena: x-key offset of the selected object (stored key - x_off = true block x)
 };
 
 __device__ __forceinline__ int find_slot(const ExtractCtx& c, uint64_t key) {
@@ -224,7 +225,7 @@ __global__ void __launch_bounds__(128) mc_vertices_kernel(ExtractCtx c, const ui
             const uint4 r0 = blk[rec_index(x, y, z)];
             const uint4 r1 = block_ptr(c.chunks, nslot[nb])[rec_index(q[0] & 15, q[1] & 15, q[2] & 15)];
             const double f0 = fabs((double)__uint_as_float(r0.x)), f1 = fabs((double)__uint_as_float(r1.x));
-            const int g[3] = {kx * kRes + x, ky * kRes + y, kz * kRes + z};
+            const int g[3] = {(kx - c.x_off) * kRes + x, ky * kRes + y, kz * kRes + z};
             double pt[3];
 #pragma unroll
             for (int k = 0; k < 3; ++k) pt[k] = __dadd_rn(c.half, __dmul_rn(c.vl, (double)g[k]));
@@ -451,7 +452,7 @@ __global__ void __launch_bounds__(256) pc_extract_kernel(ExtractCtx c, const int
         const int x = vox >> 8, y = (vox >> 4) & 15, z = vox & 15;
         const uint4 r0 = blk[rec_index(x, y, z)];
         const double r0a = fabs((double)__uint_as_float(r0.x));
-        const int g[3] = {kx * kRes + x, ky * kRes + y, kz * kRes + z};
+        const int g[3] = {(kx - c.x_off) * kRes + x, ky * kRes + y, kz * kRes + z};
         double p0[3];
 #pragma unroll
         for (int j = 0; j < 3; ++j) p0[j] = __dadd_rn(c.half, __dmul_rn(c.vl, (double)g[j]));
@@ -487,7 +488,9 @@ static int make_ctx(otslam_volume* v, ExtractCtx& c) {
     const uint64_t* dk = nullptr;
     const int32_t* ds = nullptr;
     int n = 0;
-    OT_TRY(volume_sorted_blocks_device(v, &dk, &ds, &n));
+    int x_off = 0;
+    OT_TRY(volume_selected_blocks_device(v, &dk, &ds, &n, &x_off));
+    c.x_off = x_off;
     c.keys = v->d_keys; c.vals = v->d_vals; c.cap_mask = v->cap - 1; c.chunks = v->d_chunks;
     c.bkeys = dk; c.bslots = ds; c.n = n; c.slab = v->slab;
     c.vl = v->voxel_length; c.half = 0.5 * v->voxel_length;
@@ -517,12 +520,13 @@ int otslam_volume_extract_mesh(otslam_volume* v, int64_t* n_vertices, int64_t* n
     DevBuf<uint8_t> cube;
     DevBuf<int> tri_count, vcount;
     DevBuf<int64_t> vbase, fbase, vbase_slot;
-    OT_CUDA(flags.alloc((size_t)n * kFlagWords));
-    OT_CUDA(wprefix.alloc((size_t)n * kFlagWords));
-    OT_CUDA(cube.alloc((size_t)n * kVox));
+    const size_t n_slots = (size_t)v->n_blocks;      // per-slot arrays: an arena extracts a sub-list, slots range over the pool
+    OT_CUDA(flags.alloc(n_slots * kFlagWords));
+    OT_CUDA(wprefix.alloc(n_slots * kFlagWords));
+    OT_CUDA(cube.alloc(n_slots * kVox));
     OT_CUDA(tri_count.alloc(n)); OT_CUDA(vcount.alloc(n));
-    OT_CUDA(vbase.alloc(n + 1)); OT_CUDA(fbase.alloc(n + 1)); OT_CUDA(vbase_slot.alloc(n));
-    OT_CUDA(cudaMemsetAsync(flags.p, 0, (size_t)n * kFlagWords * 4, s));
+    OT_CUDA(vbase.alloc(n + 1)); OT_CUDA(fbase.alloc(n + 1)); OT_CUDA(vbase_slot.alloc(n_slots));
+    OT_CUDA(cudaMemsetAsync(flags.p, 0, n_slots * kFlagWords * 4, s));
     mc_classify_kernel<<<n, 256, 0, s>>>(c, flags.p, cube.p, tri_count.p);
     OT_LAUNCHED();
     mc_count_kernel<<<n, 128, 0, s>>>(c.bslots, flags.p, wprefix.p, vcount.p);

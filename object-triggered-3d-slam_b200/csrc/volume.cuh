@@ -12,7 +12,7 @@ constexpr int kMaxBatch = 32;   // frames fused per block residency (one bit eac
 struct FrameDev {
     float E[12];      // rows 0..2 of extrinsic.cast<float>()           
     float es[3];      // (E * voxel_length).col(2): the per-z increment  
-    float pad;
+    int32_t key_off;  // multi-object arenas: x-key offset of the frame's object (0 for ordinary volumes)
     double pose[12];  // rows 0..2 of camera_pose = extrinsic.inverse()  
 };
 static_assert(sizeof(FrameDev) == 160, "FrameDev layout");
@@ -49,7 +49,10 @@ struct otslam_volume {
     cudaStream_t stream = nullptr, copy_stream = nullptr, pre_stream = nullptr;
     bool own_stream = true;
     int batch = otslam::kMaxBatch;
-    int zsplit = 0;                // CTAs per block along z in the integration kernel: 0 = auto, 1, 2, 4
+    int zsplit = 0;                // CTAs per block along z in the integration kernel: 0 = default (2), 1, 2, 4, 8
+    int n_objects = 0;             // > 0: multi-object arena (object id in the block key), see common.cuh
+    int sel_obj = -1;              // arena: object that extraction / export / stats address (-1 = none selected)
+    int64_t obj_frames[otslam::kMaxObjects] = {};   // frames integrated per object (the 65535 limit is per voxel)
     int64_t frames_integrated = 0;
 
     // block hash: open addressing, entry index is the handle used by the per-batch work list
@@ -117,6 +120,8 @@ struct otslam_volume {
 namespace otslam {
 // implemented in volume.cu, used by extract.cu: the allocated blocks sorted by key, in HBM (valid until the volume changes)
 int volume_sorted_blocks_device(otslam_volume* v, const uint64_t** d_keys, const int32_t** d_slots, int* n);
+// the same restricted to the selected object of a multi-object arena (x_off = the object's x-key offset; 0 otherwise)
+int volume_selected_blocks_device(otslam_volume* v, const uint64_t** d_keys, const int32_t** d_slots, int* n, int* x_off);
 // the same downloaded to the host (export_blocks)
 int volume_sorted_blocks(otslam_volume* v, std::vector<uint64_t>& keys, std::vector<int32_t>& slots);
 // knn.cu: stable LSD radix sort of (u64 key, i32 value) pairs by the low `bits` bits; result in (kb, vb), (ka, va) clobbered

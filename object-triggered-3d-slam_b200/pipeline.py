@@ -165,18 +165,90 @@ def integrate_files(volume, triples, intrinsics, T_fix, depth_scale=1000.0, dept
     return done
 
 
+def _decode_job(pool, triples, intrinsics, T_fix, skip_errors, on_error, progress):
+    """Decode every frame of one job (thread pool) and apply the per-frame error semantics in file order; returns
+    (depth [m,H,W] u16, rgb [m,H,W,3] u8, extrinsics [m,4,4]) of the frames that survive."""
+    n = len(triples)
+    dbuf = np.empty((n, intrinsics.height, intrinsics.width), np.uint16)
+    cbuf = np.empty((n, intrinsics.height, intrinsics.width, 3), np.uint8)
+    futs = [pool.submit(_decode_into, t, intrinsics, T_fix, dbuf[k], cbuf[k]) for k, t in enumerate(triples)]
+    slots, exts = [], []
+    for k, (fut, triple) in enumerate(zip(futs, triples)):
+        ext, err = fut.result()
+        if err is not None:
+            if not skip_errors:
+                for f in futs[k + 1:]:
+                    f.cancel()
+                raise err
+            if on_error:
+                on_error(triple[3], err)
+            continue
+        slots.append(k); exts.append(ext)
+        if progress:
+            progress(triple[3], k + 1, n)
+    if len(slots) != n:
+        dbuf, cbuf = np.ascontiguousarray(dbuf[slots]), np.ascontiguousarray(cbuf[slots])
+    return dbuf, cbuf, (np.stack(exts) if exts else np.zeros((0, 4, 4)))
+
+
+def interleave_plan(counts, batch=32):
+    """Order in which the frames of several objects enter an arena: batches of `batch` frames drawn round-robin in runs of
+    batch // n_active frames per object, each object's own order preserved.  Returns [(object, frame index)]."""
+    nxt = [0] * len(counts)
+    order = []
+    while True:
+        active = [o for o, c in enumerate(counts) if nxt[o] < c]
+        if not active:
+            return order
+        run = max(1, batch // len(active))
+        for o in active:
+            take = min(run, counts[o] - nxt[o])
+            order += [(o, nxt[o] + k) for k in range(take)]
+            nxt[o] += take
+
+
 def integrate_many(jobs, max_workers=None):
-    """Config 3 (multi_reconstruct_rgbd_filter.py: several objects, each its own volume): run the
-    independent per-object frame loops CONCURRENTLY on one GPU.  Each volume owns its CUDA streams and
-    the C-ABI calls release the GIL, so the kernels of small per-object volumes (which alone cannot
-    fill 148 SMs) overlap on the device.  jobs = [(volume, triples, kwargs)]; returns the frame counts
-    in job order.  Results are identical to running the jobs one after the other."""
+    """Config 3 (multi_reconstruct_rgbd_filter.py:139-145: several objects, each its own volume, one after the other):
+    the objects' frame loops run TOGETHER through one multi-object arena -- one block hash with the object id in the block
+    key, one work list and ONE integration launch per batch over the union of the objects' touched blocks (a single small
+    object cannot fill 148 SMs).  jobs = [(compat ScalableTSDFVolume, triples, kwargs of integrate_files)]; all jobs share
+    the camera and the voxel parameters.  Afterwards every job's volume addresses its own object of the arena (extraction,
+    export and statistics are per object); each object's result is bit-identical to a volume of its own.  Returns the frame
+    counts in job order."""
     from concurrent.futures import ThreadPoolExecutor
+    from .volume import ArenaView, TSDFVolume
     if not jobs:
         return []
-    with ThreadPoolExecutor(max_workers=max_workers or len(jobs)) as ex:
-        futs = [ex.submit(integrate_files, vol, triples, **kw) for vol, triples, kw in jobs]
-        return [f.result() for f in futs]
+    if len(jobs) == 1 or len(jobs) > 8:
+        return [integrate_files(vol, triples, **kw) for vol, triples, kw in jobs]
+    v0, kw0 = jobs[0][0], jobs[0][2]
+    intr = kw0["intrinsics"]
+    for vol, _, kw in jobs:
+        if (vol.voxel_length, vol.sdf_trunc, vol.color_type) != (v0.voxel_length, v0.sdf_trunc, v0.color_type) or \
+                kw["intrinsics"].fxfycxcy() != intr.fxfycxcy() or (kw["intrinsics"].width, kw["intrinsics"].height) != (intr.width, intr.height):
+            return [integrate_files(vol, triples, **kw) for vol, triples, kw in jobs]      # not one arena's worth: run them apart
+    with ThreadPoolExecutor(max_workers=max_workers or _decode_workers()) as pool:
+        decoded = [_decode_job(pool, triples, kw["intrinsics"], kw["T_fix"], kw.get("skip_errors", False), kw.get("on_error"),
+                               kw.get("progress")) for _, triples, kw in jobs]
+    counts = [len(d[2]) for d in decoded]
+    color = v0._vol._h is not None and v0.color_type.name == "RGB8"
+    arena = TSDFVolume(v0.voxel_length, v0.sdf_trunc, color=color, device=v0._vol.device)
+    arena.set_objects(len(jobs))
+    order = interleave_plan(counts)
+    if order:
+        objs = np.array([o for o, _ in order], np.int32)
+        depth = np.empty((len(order),) + decoded[0][0].shape[1:], np.uint16)
+        rgb = np.empty((len(order),) + decoded[0][1].shape[1:], np.uint8)
+        ext = np.empty((len(order), 4, 4), np.float64)
+        for o in range(len(jobs)):
+            sel = np.nonzero(objs == o)[0]
+            depth[sel], rgb[sel], ext[sel] = decoded[o][0][:len(sel)], decoded[o][1][:len(sel)], decoded[o][2][:len(sel)]
+        arena.integrate_batch(depth, rgb if color else None, intr.fxfycxcy(), ext, kw0.get("depth_scale", 1000.0),
+                              kw0.get("depth_trunc", 3.0), object_ids=objs)
+    for o, (vol, _, _) in enumerate(jobs):
+        vol._vol.close()
+        vol._vol = ArenaView(arena, o)
+    return counts
 
 
 def stdout_progress(fmt):

@@ -130,9 +130,20 @@ class TSDFVolume:
         k, e = self._intr(intr), np.ascontiguousarray(extrinsic, np.float64).reshape(16)
         _lib.check(_lib.lib.otslam_volume_integrate_f32(self._h, _lib.ptr(d), _lib.ptr(c), W, H, _lib.ptr(k), _lib.ptr(e)))
 
-    def integrate_batch(self, depth, rgb, intr, extrinsics, depth_scale=1000.0, depth_trunc=3.0):
+    # ---- multi-object arena (config 3): several objects' volumes in one block hash, object id in the block key -----------
+    def set_objects(self, n_objects):
+        """Turn this (empty) volume into an arena of n_objects independent objects (otslam_volume_set_objects)."""
+        _lib.check(_lib.lib.otslam_volume_set_objects(self._h, int(n_objects)))
+        self.n_objects = int(n_objects)
+
+    def select_object(self, obj):
+        """The object that extraction / export_blocks / stats / num_blocks address from now on."""
+        _lib.check(_lib.lib.otslam_volume_select_object(self._h, int(obj)))
+
+    def integrate_batch(self, depth, rgb, intr, extrinsics, depth_scale=1000.0, depth_trunc=3.0, object_ids=None):
         """depth [n,H,W] u16, rgb [n,H,W,3] u8: numpy arrays / CPU torch tensors (host path, copies
-        pipelined inside the call) or CUDA torch tensors (already resident in HBM)."""
+        pipelined inside the call) or CUDA torch tensors (already resident in HBM).  object_ids [n] i32 (arenas only):
+        the object each frame belongs to."""
         n, H, W = int(depth.shape[0]), int(depth.shape[1]), int(depth.shape[2])
         on_dev = hasattr(depth, "is_cuda") and depth.is_cuda
         if isinstance(depth, np.ndarray):
@@ -148,6 +159,12 @@ class TSDFVolume:
         e = np.ascontiguousarray(extrinsics, np.float64).reshape(n, 16)
         if on_dev:
             self._after_torch_stream(depth)       # frames produced on a torch stream (copy, NCCL gather, rendering)
+        if object_ids is not None:
+            ids = np.ascontiguousarray(object_ids, np.int32).reshape(n)
+            _lib.check(_lib.lib.otslam_volume_integrate_batch_objects(
+                self._h, n, _lib.ptr(depth), _lib.ptr(rgb), W, H, _lib.ptr(k), _lib.ptr(e), _lib.ptr(ids), float(depth_scale),
+                float(depth_trunc), _lib.MEM_DEVICE if on_dev else _lib.MEM_HOST))
+            return
         _lib.check(_lib.lib.otslam_volume_integrate_batch(self._h, n, _lib.ptr(depth), _lib.ptr(rgb), W, H, _lib.ptr(k),
                                                           _lib.ptr(e), float(depth_scale), float(depth_trunc),
                                                           _lib.MEM_DEVICE if on_dev else _lib.MEM_HOST))
@@ -254,3 +271,42 @@ class TSDFVolume:
         ek = np.empty((n.value, 4), np.int32)
         _lib.check(_lib.lib.otslam_volume_points_copy(self._h, _lib.ptr(pts), _lib.ptr(cols), _lib.ptr(ek)))
         return pts, cols, ek
+
+
+
+class ArenaView:
+    """One object of a multi-object arena, with the interface of a TSDFVolume of its own: what the compat
+    ScalableTSDFVolume of a config-3 job is re-bound to after pipeline.integrate_many (the objects' frames went through
+    ONE work list / integration launch per batch; extraction, export and statistics address this object only)."""
+
+    def __init__(self, arena, obj):
+        self._arena, self._obj = arena, int(obj)
+        self.voxel_length, self.sdf_trunc, self.device = arena.voxel_length, arena.sdf_trunc, arena.device
+
+    def __getattr__(self, name):
+        attr = getattr(self._arena, name)
+        if not callable(attr):
+            return attr
+
+        def call(*a, **k):
+            self._arena.select_object(self._obj)
+            return attr(*a, **k)
+        return call
+
+    def integrate_batch(self, depth, rgb, intr, extrinsics, depth_scale=1000.0, depth_trunc=3.0):
+        self._arena.integrate_batch(depth, rgb, intr, extrinsics, depth_scale, depth_trunc,
+                                    object_ids=np.full(int(depth.shape[0]), self._obj, np.int32))
+
+    def integrate_u16(self, depth, rgb, intr, extrinsic, depth_scale=1000.0, depth_trunc=3.0):
+        d = np.ascontiguousarray(depth, np.uint16)[None]
+        c = None if rgb is None else np.ascontiguousarray(rgb, np.uint8)[None]
+        self.integrate_batch(d, c, intr, np.asarray(extrinsic, np.float64).reshape(1, 4, 4), depth_scale, depth_trunc)
+
+    def integrate_f32(self, *a, **k):
+        raise RuntimeError("an arena object integrates raw u16 depth only")
+
+    def reset(self):
+        raise RuntimeError("objects of a multi-object arena cannot be reset individually")
+
+    def close(self):
+        pass            # the arena lives as long as one of its views does

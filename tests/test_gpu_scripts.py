@@ -144,13 +144,13 @@ def test_hybrid_map_script(tmp_path):
 
 
 def test_multi_objects_in_parallel_match_sequential(capture):
-    """Config 3: independent per-object volumes integrated concurrently (threads + per-volume CUDA
-    streams) give exactly the PLYs of the sequential run."""
+    """Config 3: the objects' frame loops through one multi-object arena (object id in the block key, one work list and one
+    integration launch per batch) give exactly the PLYs of the reference-style sequential run."""
     import otslam_b200.o3d_compat as o3d
     base, seqs = capture
     ranges = {"par_a": [1, 4], "par_b": [5, 8], "par_c": [9, 12], "par_d": [2, 11]}
     env = {"OTSLAM_BASE_DIR": base, "OTSLAM_OBJECT_RANGES": json.dumps(ranges), "OTSLAM_SAMPLE_SEED": "3"}
-    run_script("3d_model/multi_reconstruct_rgbd_filter.py", env)
+    run_script("3d_model/multi_reconstruct_rgbd_filter.py", dict(env, OTSLAM_PARALLEL_OBJECTS="0"))
     seq_out = {k: open(os.path.join(base, "3d_reconst", f"{k}.ply"), "rb").read() for k in ranges}
     for k in ranges:
         os.remove(os.path.join(base, "3d_reconst", f"{k}.ply"))

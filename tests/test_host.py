@@ -292,3 +292,15 @@ def test_capture_tool_name_patterns_and_tf_pose(tmp_path):
     c = cv2.imread(os.path.join(str(tmp_path / "gt"), "color", "gt_color_0007.png"), cv2.IMREAD_UNCHANGED)
     assert (c[..., ::-1] == rgb).all()                     # PNG colour is lossless
     assert capture.save_frame(str(tmp_path / "s"), "Object_3", 12, rgb, depth, T) == "Object_3_12"
+
+
+def test_interleave_plan_round_robin_runs():
+    """pipeline.interleave_plan (config 3 arena ingest): every frame once, per-object order kept, 32-frame batches shared."""
+    from otslam_b200 import pipeline
+    for counts in ([150, 150, 150, 150], [5, 0, 40], [1], [33, 2, 2, 2, 2, 2, 2, 2], []):
+        order = pipeline.interleave_plan(counts)
+        assert sorted(order) == sorted((o, k) for o, c in enumerate(counts) for k in range(c))
+        for o in range(len(counts)):
+            assert [k for oo, k in order if oo == o] == list(range(counts[o]))
+    first = pipeline.interleave_plan([150, 150, 150, 150])[:32]
+    assert [o for o, _ in first] == [0] * 8 + [1] * 8 + [2] * 8 + [3] * 8

@@ -4,7 +4,7 @@
 out=gpurun_out/emulate_matrix.txt
 : > $out
 for w in 1 2 4 8; do
-  for z in 0 2 4 8; do
+  for z in ${ZS_LIST:-0 2 4}; do
     if [ $w = 1 ] && [ $z = 8 ]; then continue; fi
     python bench.py --steps 5 --warmup 3 --no-post --no-cpu --no-e2e --hd-frames 0 --emulate-world $w --zsplit $z "$@" > gpurun_out/em.json 2> gpurun_out/em.err || { echo "w=$w z=$z FAILED" >> $out; tail -3 gpurun_out/em.err >> $out; continue; }
     python - "$w" "$z" >> $out <<'PY'
