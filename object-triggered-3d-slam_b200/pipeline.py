@@ -53,11 +53,74 @@ def read_pose(path):
     return np.loadtxt(path)
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# Raw side-car of a capture tree ("streaming ingest"): JPEG / PNG decoding is what bounds the drop-in
+# scripts end to end (~1.8 k frames/s on 16 host threads against ~50 k frames/s of GPU integration).  With
+# OTSLAM_SIDECAR=1 the first pass over a tree stores every decoded frame pair next to it
+#     <base>/.otslam_raw/<depth file stem>.raw = header | depth u16 [H][W] | rgb u8 [H][W][3]
+# (exactly the arrays the decoders produced, so the volumes are identical), keyed by the size and mtime of the two source
+# files; later passes read the raw bytes straight into the staging buffers.  Poses stay in their text files.
+# ---------------------------------------------------------------------------------------------------------------------
+_SIDECAR_MAGIC = b"OTSLAMRAW1\n"
+_SIDECAR_HDR = 64
+
+
+def sidecar_enabled():
+    return os.environ.get("OTSLAM_SIDECAR", "0") not in ("", "0")
+
+
+def _sidecar_path(depth_path):
+    d = os.path.dirname(os.path.abspath(depth_path))
+    return os.path.join(os.path.dirname(d), ".otslam_raw", os.path.splitext(os.path.basename(depth_path))[0] + ".raw")
+
+
+def _sidecar_tag(cp, dp, H, W):
+    sc, sd = os.stat(cp), os.stat(dp)
+    return np.array([H, W, sc.st_size, sc.st_mtime_ns, sd.st_size, sd.st_mtime_ns], np.int64)
+
+
+def _sidecar_load(cp, dp, depth_out, color_out):
+    """True when a valid side-car filled the two staging slots."""
+    path = _sidecar_path(dp)
+    try:
+        with open(path, "rb", buffering=0) as f:
+            hdr = f.read(_SIDECAR_HDR)
+            if len(hdr) != _SIDECAR_HDR or not hdr.startswith(_SIDECAR_MAGIC):
+                return False
+            H, W = depth_out.shape
+            tag = np.frombuffer(hdr, np.int64, 6, len(_SIDECAR_MAGIC) + (-len(_SIDECAR_MAGIC)) % 8)
+            if not (tag == _sidecar_tag(cp, dp, H, W)).all():
+                return False                                     # sources changed (or another image size): decode again
+            return f.readinto(memoryview(depth_out).cast("B")) == H * W * 2 and f.readinto(memoryview(color_out).cast("B")) == H * W * 3
+    except OSError:
+        return False
+
+
+def _sidecar_store(cp, dp, depth, color):
+    path = _sidecar_path(dp)
+    try:
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        H, W = depth.shape
+        pad = (-len(_SIDECAR_MAGIC)) % 8
+        hdr = _SIDECAR_MAGIC + b"\0" * pad + _sidecar_tag(cp, dp, H, W).tobytes()
+        tmp = f"{path}.{os.getpid()}.tmp"
+        with open(tmp, "wb") as f:
+            f.write(hdr + b"\0" * (_SIDECAR_HDR - len(hdr)))
+            f.write(memoryview(np.ascontiguousarray(depth)).cast("B"))
+            f.write(memoryview(np.ascontiguousarray(color)).cast("B"))
+        os.replace(tmp, path)
+    except OSError:
+        pass                                                     # read-only dataset: keep decoding
+
+
 def _decode_into(triple, intrinsics, T_fix, depth_out, color_out):
     """load_frame, decoding straight into one slot of the chunk's staging buffers (no per-frame arrays, no np.stack)."""
     import cv2
     cp, dp, pp, _ = triple
     try:
+        if sidecar_enabled() and depth_out.shape == (intrinsics.height, intrinsics.width) and os.path.exists(cp) and os.path.exists(dp) \
+                and _sidecar_load(cp, dp, depth_out, color_out):
+            return np.linalg.inv(read_pose(pp) @ T_fix), None
         c = cv2.imread(cp, cv2.IMREAD_UNCHANGED) if os.path.exists(cp) else None
         d = cv2.imread(dp, cv2.IMREAD_UNCHANGED) if os.path.exists(dp) else None
         for path, a in ((cp, c), (dp, d)):
@@ -72,6 +135,8 @@ def _decode_into(triple, intrinsics, T_fix, depth_out, color_out):
             raise RuntimeError(_FMT)
         cv2.cvtColor(c, cv2.COLOR_BGRA2RGB if c.shape[2] == 4 else cv2.COLOR_BGR2RGB, dst=color_out)
         np.copyto(depth_out, d)
+        if sidecar_enabled():
+            _sidecar_store(cp, dp, depth_out, color_out)
         return extrinsic, None
     except Exception as err:  # noqa: BLE001
         return None, err

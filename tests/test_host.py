@@ -304,3 +304,37 @@ def test_interleave_plan_round_robin_runs():
             assert [k for oo, k in order if oo == o] == list(range(counts[o]))
     first = pipeline.interleave_plan([150, 150, 150, 150])[:32]
     assert [o for o, _ in first] == [0] * 8 + [1] * 8 + [2] * 8 + [3] * 8
+
+
+def test_raw_sidecar_round_trip_and_invalidation(tmp_path, monkeypatch):
+    """OTSLAM_SIDECAR=1: the first decode of a capture triple stores the decoded arrays; later loads return exactly those
+    arrays without decoding; touching a source file invalidates the side-car."""
+    import cv2
+    from otslam_b200 import capture, pipeline, synth
+    rng = np.random.default_rng(1)
+    H, W = 48, 64
+    rgb = rng.integers(0, 255, (H, W, 3), dtype=np.uint8)
+    depth = rng.integers(300, 3000, (H, W), dtype=np.uint16)
+    base = str(tmp_path)
+    capture.save_frame(base, "Object_0", 1, rgb, depth, np.eye(4))
+    t = (os.path.join(base, "color", "Object_0_1.jpg"), os.path.join(base, "depth", "Object_0_1.png"),
+         os.path.join(base, "poses", "Object_0_1.txt"), 1)
+    intr = o3d.camera.PinholeCameraIntrinsic(W, H, 50.0, 50.0, 32.5, 24.5)
+    d0, c0 = np.empty((H, W), np.uint16), np.empty((H, W, 3), np.uint8)
+    monkeypatch.setenv("OTSLAM_SIDECAR", "0")
+    e0, err = pipeline._decode_into(t, intr, synth.T_FIX, d0, c0)
+    assert err is None and not os.path.exists(pipeline._sidecar_path(t[1]))
+    monkeypatch.setenv("OTSLAM_SIDECAR", "1")
+    d1, c1 = np.empty_like(d0), np.empty_like(c0)
+    e1, err = pipeline._decode_into(t, intr, synth.T_FIX, d1, c1)          # decodes, writes the side-car
+    assert err is None and os.path.exists(pipeline._sidecar_path(t[1])) and (d1 == d0).all() and (c1 == c0).all()
+    calls = []
+    real = cv2.imread
+    monkeypatch.setattr(cv2, "imread", lambda *a, **k: calls.append(a) or real(*a, **k))
+    d2, c2 = np.zeros_like(d0), np.zeros_like(c0)
+    e2, err = pipeline._decode_into(t, intr, synth.T_FIX, d2, c2)          # served from the side-car
+    assert err is None and not calls and (d2 == d0).all() and (c2 == c0).all() and (e2 == e0).all()
+    os.utime(t[1], ns=(1, 1))                                              # the depth PNG "changed"
+    d3, c3 = np.zeros_like(d0), np.zeros_like(c0)
+    _, err = pipeline._decode_into(t, intr, synth.T_FIX, d3, c3)
+    assert err is None and len(calls) == 2 and (d3 == d0).all()
