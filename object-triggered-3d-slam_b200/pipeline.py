@@ -61,8 +61,8 @@ def read_pose(path):
 # (exactly the arrays the decoders produced, so the volumes are identical), keyed by the size and mtime of the two source
 # files; later passes read the raw bytes straight into the staging buffers.  Poses stay in their text files.
 # ---------------------------------------------------------------------------------------------------------------------
-_SIDECAR_MAGIC = b"OTSLAMRAW1\n"
-_SIDECAR_HDR = 64
+_SIDECAR_MAGIC = b"OTSLAMRAW2\n\0\0\0\0\0"      # 16 bytes
+_SIDECAR_HDR = 256                                  # magic | 8 x int64 tag | 16 x float64 pose_ros | padding
 
 
 def sidecar_enabled():
@@ -74,42 +74,41 @@ def _sidecar_path(depth_path):
     return os.path.join(os.path.dirname(d), ".otslam_raw", os.path.splitext(os.path.basename(depth_path))[0] + ".raw")
 
 
-def _sidecar_tag(cp, dp, H, W):
-    sc, sd = os.stat(cp), os.stat(dp)
-    return np.array([H, W, sc.st_size, sc.st_mtime_ns, sd.st_size, sd.st_mtime_ns], np.int64)
+def _sidecar_tag(cp, dp, pp, H, W):
+    sc, sd, sp = os.stat(cp), os.stat(dp), os.stat(pp)
+    return np.array([H, W, sc.st_size, sc.st_mtime_ns, sd.st_size, sd.st_mtime_ns, sp.st_size, sp.st_mtime_ns], np.int64)
 
 
-def _sidecar_load(cp, dp, depth_out, color_out):
-    """True when a valid side-car filled the two staging slots."""
-    path = _sidecar_path(dp)
+def _sidecar_load(cp, dp, pp, depth_out, color_out):
+    """pose_ros (4x4) when a valid side-car filled the two staging slots, else None."""
     try:
-        with open(path, "rb", buffering=0) as f:
+        with open(_sidecar_path(dp), "rb", buffering=0) as f:
             hdr = f.read(_SIDECAR_HDR)
-            if len(hdr) != _SIDECAR_HDR or not hdr.startswith(_SIDECAR_MAGIC):
-                return False
+            if len(hdr) != _SIDECAR_HDR or hdr[:16] != _SIDECAR_MAGIC:
+                return None
             H, W = depth_out.shape
-            tag = np.frombuffer(hdr, np.int64, 6, len(_SIDECAR_MAGIC) + (-len(_SIDECAR_MAGIC)) % 8)
-            if not (tag == _sidecar_tag(cp, dp, H, W)).all():
-                return False                                     # sources changed (or another image size): decode again
-            return f.readinto(memoryview(depth_out).cast("B")) == H * W * 2 and f.readinto(memoryview(color_out).cast("B")) == H * W * 3
+            if not (np.frombuffer(hdr, np.int64, 8, 16) == _sidecar_tag(cp, dp, pp, H, W)).all():
+                return None                                      # a source file changed (or another image size): decode again
+            if f.readinto(memoryview(depth_out).cast("B")) != H * W * 2 or f.readinto(memoryview(color_out).cast("B")) != H * W * 3:
+                return None
+            return np.frombuffer(hdr, np.float64, 16, 80).reshape(4, 4)
     except OSError:
-        return False
+        return None
 
 
-def _sidecar_store(cp, dp, depth, color):
+def _sidecar_store(cp, dp, pp, depth, color, pose_ros):
     path = _sidecar_path(dp)
     try:
         os.makedirs(os.path.dirname(path), exist_ok=True)
         H, W = depth.shape
-        pad = (-len(_SIDECAR_MAGIC)) % 8
-        hdr = _SIDECAR_MAGIC + b"\0" * pad + _sidecar_tag(cp, dp, H, W).tobytes()
+        hdr = _SIDECAR_MAGIC + _sidecar_tag(cp, dp, pp, H, W).tobytes() + np.ascontiguousarray(pose_ros, np.float64).tobytes()
         tmp = f"{path}.{os.getpid()}.tmp"
         with open(tmp, "wb") as f:
             f.write(hdr + b"\0" * (_SIDECAR_HDR - len(hdr)))
             f.write(memoryview(np.ascontiguousarray(depth)).cast("B"))
             f.write(memoryview(np.ascontiguousarray(color)).cast("B"))
         os.replace(tmp, path)
-    except OSError:
+    except (OSError, ValueError):
         pass                                                     # read-only dataset: keep decoding
 
 
@@ -118,9 +117,10 @@ def _decode_into(triple, intrinsics, T_fix, depth_out, color_out):
     import cv2
     cp, dp, pp, _ = triple
     try:
-        if sidecar_enabled() and depth_out.shape == (intrinsics.height, intrinsics.width) and os.path.exists(cp) and os.path.exists(dp) \
-                and _sidecar_load(cp, dp, depth_out, color_out):
-            return np.linalg.inv(read_pose(pp) @ T_fix), None
+        if sidecar_enabled() and depth_out.shape == (intrinsics.height, intrinsics.width):
+            pose_ros = _sidecar_load(cp, dp, pp, depth_out, color_out)
+            if pose_ros is not None:
+                return np.linalg.inv(pose_ros @ T_fix), None
         c = cv2.imread(cp, cv2.IMREAD_UNCHANGED) if os.path.exists(cp) else None
         d = cv2.imread(dp, cv2.IMREAD_UNCHANGED) if os.path.exists(dp) else None
         for path, a in ((cp, c), (dp, d)):
@@ -136,7 +136,7 @@ def _decode_into(triple, intrinsics, T_fix, depth_out, color_out):
         cv2.cvtColor(c, cv2.COLOR_BGRA2RGB if c.shape[2] == 4 else cv2.COLOR_BGR2RGB, dst=color_out)
         np.copyto(depth_out, d)
         if sidecar_enabled():
-            _sidecar_store(cp, dp, depth_out, color_out)
+            _sidecar_store(cp, dp, pp, depth_out, color_out, pose_ros)
         return extrinsic, None
     except Exception as err:  # noqa: BLE001
         return None, err
