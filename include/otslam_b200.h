@@ -171,6 +171,9 @@ int otslam_volume_mesh_sample(otslam_volume* v, int64_t n_samples, uint64_t seed
 /* volume.extract_point_cloud() (named by north_star; zero crossings along +x/+y/+z) */
 int otslam_volume_extract_points(otslam_volume* v, int64_t* n_points);
 int otslam_volume_points_copy(otslam_volume* v, double* points, double* colors, int32_t* edge_keys);   /* host or device */
+/* the normals extract_point_cloud() attaches: normalised central differences (+-0.99 voxel) of the trilinearly interpolated
+ * TSDF at every point of the last extraction (Open3D GetNormalAt / GetTSDFAt); normals [n][3], host or device */
+int otslam_volume_points_normals(otslam_volume* v, double* normals);
 
 /* ---- stateless image / cloud operators (host in, host out) */
 /* RGBDImage.create_from_color_and_depth depth half (reconstruct_rgbd.py:99-104) */

@@ -65,6 +65,7 @@ _SIGS = {
     "otslam_volume_mesh_sample": (_i, [_vp, _i64, _u64, _vp, _vp, _vp]),
     "otslam_volume_extract_points": (_i, [_vp, C.POINTER(_i64)]),
     "otslam_volume_points_copy": (_i, [_vp, _vp, _vp, _vp]),
+    "otslam_volume_points_normals": (_i, [_vp, _vp]),
     "otslam_depth_convert": (_i, [_vp, _i64, _d, _d, _vp, _i]),
     "otslam_backproject_rgbd": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, C.POINTER(_i64), _i]),
     "otslam_mesh_vertex_normals": (_i, [_vp, _i64, _vp, _i64, _vp, _i]),

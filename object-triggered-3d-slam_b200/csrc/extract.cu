@@ -57,7 +57,7 @@ struct ExtractCtx {
     const int32_t* bslots;    // [n] their pool slots
     int n;
     SlabSpec slab;
-    double vl, half;
+    double vl, half, unit;    // voxel length, half of it, block edge length
     int x_off;                // multi-object arena: x-key offset of the selected object (stored key - x_off = true block x)
 };
 
@@ -471,11 +471,13 @@ __global__ void __launch_bounds__(256) pc_extract_kernel(ExtractCtx c, const int
         const int vox = 16 * t + k;
         const int x = vox >> 8, y = (vox >> 4) & 15, z = vox & 15;
         const uint4 r0 = blk[rec_index(x, y, z)];
-        const double r0a = fabs((double)__uint_as_float(r0.x));
+        const float r0a = fabsf(__uint_as_float(r0.x));                  // Open3D keeps r0, r1 and their sum in FP32
         const int g[3] = {(kx - c.x_off) * kRes + x, ky * kRes + y, kz * kRes + z};
+        const int loc[3] = {x, y, z}, bk[3] = {kx - c.x_off, ky, kz};
         double p0[3];
 #pragma unroll
-        for (int j = 0; j < 3; ++j) p0[j] = __dadd_rn(c.half, __dmul_rn(c.vl, (double)g[j]));
+        for (int j = 0; j < 3; ++j)     // (half + vl * x_local) + block_index * unit_length, as ExtractPointCloud forms it
+            p0[j] = __dadd_rn(__dadd_rn(c.half, __dmul_rn(c.vl, (double)loc[j])), __dmul_rn((double)bk[j], c.unit));
         const uint32_t w0 = rec_weight(r0);
         for (int a = 0; a < 3; ++a) {
             if (!(h & (1u << a))) continue;
@@ -483,24 +485,78 @@ __global__ void __launch_bounds__(256) pc_extract_kernel(ExtractCtx c, const int
             q[a] += 1;
             const int s = nslot[(q[0] >> 4) | ((q[1] >> 4) << 1) | ((q[2] >> 4) << 2)];
             const uint4 r1 = block_ptr(c.chunks, s)[rec_index(q[0] & 15, q[1] & 15, q[2] & 15)];
-            const double r1a = fabs((double)__uint_as_float(r1.x));
+            const float r1a = fabsf(__uint_as_float(r1.x));
             const uint32_t w1 = rec_weight(r1);
-            const double rs = __dadd_rn(r0a, r1a);
+            const float rs = __fadd_rn(r0a, r1a);
             double p[3] = {p0[0], p0[1], p0[2]};
             const double p1a = __dadd_rn(p0[a], c.vl);
-            p[a] = __ddiv_rn(__dadd_rn(__dmul_rn(p0[a], r1a), __dmul_rn(p1a, r0a)), rs);
+            p[a] = __ddiv_rn(__dadd_rn(__dmul_rn(p0[a], (double)r1a), __dmul_rn(p1a, (double)r0a)), (double)rs);
             const uint32_t s0[3] = {r0.y & 0xFFFFFFu, r0.z & 0xFFFFFFu, r0.w & 0xFFFFFFu};
             const uint32_t s1[3] = {r1.y & 0xFFFFFFu, r1.z & 0xFFFFFFu, r1.w & 0xFFFFFFu};
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
                 pts[3 * o + j] = p[j];
-                const double c0 = __ddiv_rn((double)s0[j], (double)w0), c1 = __ddiv_rn((double)s1[j], (double)w1);
-                cols[3 * o + j] = __ddiv_rn(__ddiv_rn(__dadd_rn(__dmul_rn(c0, r1a), __dmul_rn(c1, r0a)), rs), 255.0);
+                // voxel colour = exact sum / count in FP64 (the reference keeps an FP64 running mean), cast to float as
+                // Open3D's c0, c1 are; interpolation and the division by 255.0f in FP32
+                const float c0 = (float)__ddiv_rn((double)s0[j], (double)w0), c1 = (float)__ddiv_rn((double)s1[j], (double)w1);
+                cols[3 * o + j] = (double)__fdiv_rn(__fdiv_rn(__fadd_rn(__fmul_rn(c0, r1a), __fmul_rn(c1, r0a)), rs), 255.0f);
             }
             if (ekeys) { ekeys[4 * o] = g[0]; ekeys[4 * o + 1] = g[1]; ekeys[4 * o + 2] = g[2]; ekeys[4 * o + 3] = a; }
             ++o;
         }
     }
+}
+
+// ---- ScalableTSDFVolume::GetNormalAt for extracted points (the normals ExtractPointCloud attaches): central differences
+// of the trilinearly interpolated TSDF (GetTSDFAt) at +-0.99 voxel, normalised.  Voxels of absent blocks read 0.
+__device__ double tsdf_at(const ExtractCtx& c, const double p[3]) {
+    double pg[3], r[3];
+    int index0[3], idx0[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const double pl = __dsub_rn(p[i], c.half);
+        index0[i] = (int)floor(__ddiv_rn(pl, c.unit));
+        pg[i] = __ddiv_rn(__dsub_rn(pl, __dmul_rn((double)index0[i], c.unit)), c.vl);
+    }
+    if (!key_in_range(index0[0] + c.x_off, index0[1], index0[2]) || find_slot(c, pack_key(index0[0] + c.x_off, index0[1], index0[2])) < 0) return 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        idx0[i] = min(max((int)floor(pg[i]), 0), kRes - 1);
+        r[i] = __dsub_rn(pg[i], (double)idx0[i]);
+    }
+    double f[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        int v[3] = {idx0[0] + ((q ^ (q >> 1)) & 1), idx0[1] + ((q >> 1) & 1), idx0[2] + ((q >> 2) & 1)};
+        int b[3] = {index0[0], index0[1], index0[2]};
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            if (v[j] >= kRes) { v[j] -= kRes; b[j] += 1; }
+        const int s = key_in_range(b[0] + c.x_off, b[1], b[2]) ? find_slot(c, pack_key(b[0] + c.x_off, b[1], b[2])) : -1;
+        f[q] = s >= 0 ? (double)__uint_as_float(block_ptr(c.chunks, s)[rec_index(v[0], v[1], v[2])].x) : 0.0;
+    }
+    const double o0 = __dsub_rn(1.0, r[0]), o1 = __dsub_rn(1.0, r[1]), o2 = __dsub_rn(1.0, r[2]);
+    auto lerp2 = [&](double a, double b) { return __dadd_rn(__dmul_rn(o2, a), __dmul_rn(r[2], b)); };
+    const double lo = __dadd_rn(__dmul_rn(o1, lerp2(f[0], f[4])), __dmul_rn(r[1], lerp2(f[3], f[7])));
+    const double hi = __dadd_rn(__dmul_rn(o1, lerp2(f[1], f[5])), __dmul_rn(r[1], lerp2(f[2], f[6])));
+    return __dadd_rn(__dmul_rn(o0, lo), __dmul_rn(r[0], hi));
+}
+
+__global__ void __launch_bounds__(128) pc_normals_kernel(ExtractCtx c, const double* __restrict__ pts, int64_t n, double gap,
+                                                         double* __restrict__ normals) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double g[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        double p0[3] = {pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]}, p1[3] = {pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
+        p0[a] = __dsub_rn(p0[a], gap);
+        p1[a] = __dadd_rn(p1[a], gap);
+        g[a] = __dsub_rn(tsdf_at(c, p1), tsdf_at(c, p0));
+    }
+    const double l = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(g[0], g[0]), __dmul_rn(g[1], g[1])), __dmul_rn(g[2], g[2])));
+#pragma unroll
+    for (int a = 0; a < 3; ++a) normals[3 * i + a] = l > 0.0 ? __ddiv_rn(g[a], l) : g[a];
 }
 
 // the sorted block list lives in HBM (volume.cu: volume_sorted_blocks_device): no host round trip of the hash table
@@ -513,7 +569,7 @@ static int make_ctx(otslam_volume* v, ExtractCtx& c) {
     c.x_off = x_off;
     c.keys = v->d_keys; c.vals = v->d_vals; c.cap_mask = v->cap - 1; c.chunks = v->d_chunks;
     c.bkeys = dk; c.bslots = ds; c.n = n; c.slab = v->slab;
-    c.vl = v->voxel_length; c.half = 0.5 * v->voxel_length;
+    c.vl = v->voxel_length; c.half = 0.5 * v->voxel_length; c.unit = v->unit_length;
     return OTSLAM_OK;
 }
 
@@ -628,6 +684,22 @@ int otslam_volume_extract_points(otslam_volume* v, int64_t* n_points) {
         OT_CUDA(cudaStreamSynchronize(s));
     }
     *n_points = np;
+    return OTSLAM_OK;
+}
+
+int otslam_volume_points_normals(otslam_volume* v, double* normals) {
+    if (!v || !normals) return set_error(OTSLAM_ERR_INVALID, "null argument");
+    OT_TRY(use_device(v->device));
+    const PointsResult& p = v->points;
+    if (p.n == 0) return OTSLAM_OK;
+    ExtractCtx c;
+    OT_TRY(make_ctx(v, c));
+    DevBuf<double> dn;
+    OT_CUDA(dn.alloc((size_t)p.n * 3));
+    pc_normals_kernel<<<(unsigned)((p.n + 127) / 128), 128, 0, v->stream>>>(c, p.d_pts, p.n, 0.99 * v->voxel_length, dn.p);
+    OT_LAUNCHED();
+    OT_CUDA(cudaMemcpyAsync(normals, dn.p, (size_t)p.n * 24, cudaMemcpyDefault, v->stream));
+    OT_CUDA(cudaStreamSynchronize(v->stream));
     return OTSLAM_OK;
 }
 

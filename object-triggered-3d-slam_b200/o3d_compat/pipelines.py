@@ -66,9 +66,11 @@ class ScalableTSDFVolume:
         return m
 
     def extract_point_cloud(self):
-        p, c, _ = self._vol.extract_point_cloud()
+        """ScalableTSDFVolume.extract_point_cloud(): zero crossings along +x/+y/+z with colours and TSDF-gradient normals."""
+        p, c, _, n = self._vol.extract_point_cloud(normals=True)
         pc = geometry.PointCloud()
         pc.points = p
+        pc.normals = n
         if self.color_type != TSDFVolumeColorType.NoColor:
             pc.colors = c
         return pc

@@ -263,14 +263,20 @@ class TSDFVolume:
         _lib.check(_lib.lib.otslam_volume_mesh_copy(self._h, _lib.ptr(verts), _lib.ptr(cols), _lib.ptr(nrm), _lib.ptr(faces), _lib.ptr(ek)))
         return verts, cols, nrm, faces, ek
 
-    def extract_point_cloud(self):
+    def extract_point_cloud(self, normals=False):
+        """(points, colours, edge keys[, normals]) of volume.extract_point_cloud(); normals = TSDF gradient at the points."""
         n = C.c_int64(0)
         _lib.check(_lib.lib.otslam_volume_extract_points(self._h, C.byref(n)))
         pts = np.empty((n.value, 3), np.float64)
         cols = np.empty((n.value, 3), np.float64)
         ek = np.empty((n.value, 4), np.int32)
         _lib.check(_lib.lib.otslam_volume_points_copy(self._h, _lib.ptr(pts), _lib.ptr(cols), _lib.ptr(ek)))
-        return pts, cols, ek
+        if not normals:
+            return pts, cols, ek
+        nrm = np.empty((n.value, 3), np.float64)
+        if n.value:
+            _lib.check(_lib.lib.otslam_volume_points_normals(self._h, _lib.ptr(nrm)))
+        return pts, cols, ek, nrm
 
 
 

@@ -519,11 +519,13 @@ void oracle_mesh_free(void* mh) { delete (Mesh*)mh; }
 
 // ScalableTSDFVolume::ExtractPointCloud (named by north_star; not called by the
 // scripts).  Per voxel, +x/+y/+z zero crossings; missing neighbour block == unobserved.
-// Output arrays sized by a first call with pts==nullptr.  Normals are not produced (A.6 is [M];
-// the reference never consumes them).
+// Output arrays sized by a first call with pts==nullptr.  Arithmetic as Open3D's ScalableTSDFVolume::ExtractPointCloud
+// does it: r0 = |f0|, r1 = |f1| and their sum are FP32; the voxel centre is
+// (half + vl * x_local) + block_index * unit_length in FP64; colours are interpolated in FP32 from the float-cast voxel
+// colours and divided by 255.0f.  Normals: oracle_volume_point_normals.
 int64_t oracle_volume_extract_points(void* h, double* pts, double* cols, int32_t* edge_keys) {
     Volume* v = (Volume*)h;
-    const double vl = v->voxel_length, half = 0.5 * vl;
+    const double vl = v->voxel_length, half = 0.5 * vl, unit = v->voxel_length * RES;
     int64_t n = 0;
     for (Block* b : sorted_blocks(v)) {
         if (!slab_owns(v, b->key)) continue;
@@ -534,7 +536,8 @@ int64_t oracle_volume_extract_points(void* h, double* pts, double* cols, int32_t
                     float w0 = b->weight[idx], f0 = b->tsdf[idx];
                     if (w0 == 0.f || !(f0 < 0.98f && f0 >= -0.98f)) continue;
                     int g[3] = {b->key.x * RES + x, b->key.y * RES + y, b->key.z * RES + z};
-                    double p0[3] = {half + vl * (double)g[0], half + vl * (double)g[1], half + vl * (double)g[2]};
+                    double p0[3] = {(half + vl * (double)x) + (double)b->key.x * unit, (half + vl * (double)y) + (double)b->key.y * unit,
+                                    (half + vl * (double)z) + (double)b->key.z * unit};
                     for (int a = 0; a < 3; ++a) {
                         int q[3] = {g[0], g[1], g[2]};
                         q[a] += 1;
@@ -542,14 +545,16 @@ int64_t oracle_volume_extract_points(void* h, double* pts, double* cols, int32_t
                         if (!fetch(v, q[0], q[1], q[2], &r)) continue;
                         float w1 = r.weight, f1 = r.tsdf;
                         if (w1 == 0.f || !(f1 < 0.98f && f1 >= -0.98f) || !(f0 * f1 < 0.f)) continue;
-                        double r0 = std::fabs((double)f0), r1 = std::fabs((double)f1);
+                        const float r0 = std::fabs(f0), r1 = std::fabs(f1);
+                        const float rs = r0 + r1;
                         if (pts) {
                             double p[3] = {p0[0], p0[1], p0[2]};
                             double p1a = p0[a] + vl;
-                            p[a] = (p0[a] * r1 + p1a * r0) / (r0 + r1);
+                            p[a] = (p0[a] * (double)r1 + p1a * (double)r0) / (double)rs;
                             for (int k = 0; k < 3; ++k) {
                                 pts[3 * n + k] = p[k];
-                                cols[3 * n + k] = ((b->color[3 * idx + k] * r1 + r.color[k] * r0) / (r0 + r1)) / 255.0;
+                                const float c0 = (float)b->color[3 * idx + k], c1 = (float)r.color[k];
+                                cols[3 * n + k] = (double)(((c0 * r1 + c1 * r0) / rs) / 255.0f);
                             }
                             if (edge_keys) { edge_keys[4 * n] = g[0]; edge_keys[4 * n + 1] = g[1]; edge_keys[4 * n + 2] = g[2]; edge_keys[4 * n + 3] = a; }
                         }
@@ -558,6 +563,53 @@ int64_t oracle_volume_extract_points(void* h, double* pts, double* cols, int32_t
                 }
     }
     return n;
+}
+
+// ScalableTSDFVolume::GetTSDFAt: trilinear interpolation of the TSDF at a world point; voxels of absent blocks read 0,
+// observed or not does not matter (Open3D ignores the weight here).
+static double tsdf_at(const Volume* v, const double p[3]) {
+    const double vl = v->voxel_length, unit = v->voxel_length * RES;
+    double pl[3], pg[3], r[3];
+    int index0[3], idx0[3];
+    for (int i = 0; i < 3; ++i) {
+        pl[i] = p[i] - 0.5 * vl;
+        index0[i] = (int)std::floor(pl[i] / unit);
+    }
+    if (v->blocks.find(Key{index0[0], index0[1], index0[2]}) == v->blocks.end()) return 0.0;
+    for (int i = 0; i < 3; ++i) {
+        pg[i] = (pl[i] - (double)index0[i] * unit) / vl;
+        idx0[i] = (int)std::floor(pg[i]);
+        if (idx0[i] < 0) idx0[i] = 0;
+        if (idx0[i] >= RES) idx0[i] = RES - 1;
+        r[i] = pg[i] - (double)idx0[i];
+    }
+    float f[8];
+    for (int q = 0; q < 8; ++q) {
+        const int sx = (q ^ (q >> 1)) & 1, sy = (q >> 1) & 1, sz = (q >> 2) & 1;     // SURVEY Appendix B corner order
+        VoxRef ref;
+        f[q] = fetch(v, index0[0] * RES + idx0[0] + sx, index0[1] * RES + idx0[1] + sy, index0[2] * RES + idx0[2] + sz, &ref) ? ref.tsdf : 0.f;
+    }
+    return (1 - r[0]) * ((1 - r[1]) * ((1 - r[2]) * f[0] + r[2] * f[4]) + r[1] * ((1 - r[2]) * f[3] + r[2] * f[7])) +
+           r[0] * ((1 - r[1]) * ((1 - r[2]) * f[1] + r[2] * f[5]) + r[1] * ((1 - r[2]) * f[2] + r[2] * f[6]));
+}
+
+// ScalableTSDFVolume::GetNormalAt for n points: central TSDF differences at +-0.99 voxel, normalised (zero stays zero)
+int oracle_volume_point_normals(void* h, const double* pts, int64_t n, double* normals) {
+    Volume* v = (Volume*)h;
+    const double gap = 0.99 * v->voxel_length;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        double g[3];
+        for (int a = 0; a < 3; ++a) {
+            double p0[3] = {pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]}, p1[3] = {pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
+            p0[a] -= gap;
+            p1[a] += gap;
+            g[a] = tsdf_at(v, p1) - tsdf_at(v, p0);
+        }
+        const double l = std::sqrt((g[0] * g[0] + g[1] * g[1]) + g[2] * g[2]);
+        for (int a = 0; a < 3; ++a) normals[3 * i + a] = l > 0.0 ? g[a] / l : g[a];
+    }
+    return 0;
 }
 
 // TriangleMesh.compute_vertex_normals (reconstruct_rgbd.py:113): un-normalised

@@ -163,6 +163,13 @@ class Volume:
         lib().oracle_volume_extract_points(self.h, _p(pts), _p(cols), _p(ek))
         return pts, cols, ek
 
+    def point_normals(self, pts):
+        """GetNormalAt for each point (the normals extract_point_cloud attaches): normalised central TSDF differences."""
+        p = np.ascontiguousarray(pts, np.float64)
+        out = np.empty_like(p)
+        lib().oracle_volume_point_normals(self.h, _p(p), C.c_int64(len(p)), _p(out))
+        return out
+
 
 def vertex_normals(verts, faces):
     v = np.ascontiguousarray(verts, np.float64)

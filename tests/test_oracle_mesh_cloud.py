@@ -91,7 +91,13 @@ def test_point_cloud_subset_of_mesh_edges():
     lookup = {tuple(k): i for i, k in enumerate(ek.tolist())}
     idx = [lookup[tuple(k)] for k in pek.tolist() if tuple(k) in lookup]
     sel = [i for i, k in enumerate(pek.tolist()) if tuple(k) in lookup]
-    assert np.abs(pts[sel] - verts[idx]).max() < 1e-9      # A.5 and A.6 interpolate the same crossing
+    assert np.abs(pts[sel] - verts[idx]).max() < 5e-7      # A.5 (FP64) and A.6 (denominator |f0| + |f1| rounded to FP32: 6e-8 relative on the coordinate) interpolate the same crossing
+    # the normals extract_point_cloud attaches (GetNormalAt): normalised TSDF gradient = the sphere's outward radial direction
+    n = v.point_normals(pts)
+    radial = pts - np.array([0, 0, 1.5])
+    radial /= np.linalg.norm(radial, axis=1, keepdims=True)
+    d = np.einsum("ij,ij->i", n, radial)      # (a projective TSDF's gradient leans towards the view ray near the silhouette)
+    assert np.allclose(np.linalg.norm(n, axis=1), 1.0) and (d > 0.7).all() and np.median(d) > 0.99
 
 
 def test_vertex_normals_known_mesh():
