@@ -52,17 +52,31 @@ def filter_and_save(mesh, obj_name, save_dir):
         return None
     print(f"   Filtering points below Z < {Z_FILTER_THRESHOLD:.2f}m...")
     seed = None if SAMPLE_SEED is None else int(SAMPLE_SEED)
-    pcd = mesh.sample_points_uniformly(number_of_points=NUMBER_OF_POINTS, seed=seed)
-    points, colors = np.asarray(pcd.points), np.asarray(pcd.colors)
-    mask = points[:, 2] >= Z_FILTER_THRESHOLD
-    filtered_pcd = o3d.geometry.PointCloud()
-    filtered_pcd.points = o3d.utility.Vector3dVector(points[mask])
-    filtered_pcd.colors = o3d.utility.Vector3dVector(colors[mask])
-    if POST_VOXEL > 0:                                     # north_star stage, off by default (the reference does not run it)
-        filtered_pcd = filtered_pcd.voxel_down_sample(POST_VOXEL)
-    if POST_SOR:
-        k, ratio = POST_SOR.split(",")
-        filtered_pcd, _ = filtered_pcd.remove_statistical_outlier(int(k), float(ratio))
+    if getattr(mesh, "_res", None) is not None and os.environ.get("OTSLAM_HOST_POST", "0") in ("", "0"):
+        # the mesh is still in HBM: sample -> z mask -> (voxel_down_sample -> remove_statistical_outlier) stay there too and the
+        # final cloud is downloaded once (otslam_b200.cloud.DeviceCloud; same kernels, bit-identical to the host-array calls)
+        from otslam_b200.cloud import DeviceCloud
+        from otslam_b200.o3d_compat.geometry import _next_seed
+        dc = DeviceCloud.sample_mesh(mesh._res[0], NUMBER_OF_POINTS, _next_seed(seed), colors=mesh.has_vertex_colors(), normals=False)
+        dc = dc.zfilter(Z_FILTER_THRESHOLD)
+        if POST_VOXEL > 0:
+            dc = dc.voxel_down_sample(POST_VOXEL)
+        if POST_SOR:
+            k, ratio = POST_SOR.split(",")
+            dc, _ = dc.remove_statistical_outlier(int(k), float(ratio))
+        filtered_pcd = dc.to_pointcloud()
+    else:
+        pcd = mesh.sample_points_uniformly(number_of_points=NUMBER_OF_POINTS, seed=seed)
+        points, colors = np.asarray(pcd.points), np.asarray(pcd.colors)
+        mask = points[:, 2] >= Z_FILTER_THRESHOLD
+        filtered_pcd = o3d.geometry.PointCloud()
+        filtered_pcd.points = o3d.utility.Vector3dVector(points[mask])
+        filtered_pcd.colors = o3d.utility.Vector3dVector(colors[mask])
+        if POST_VOXEL > 0:                                     # north_star stage, off by default (the reference does not run it)
+            filtered_pcd = filtered_pcd.voxel_down_sample(POST_VOXEL)
+        if POST_SOR:
+            k, ratio = POST_SOR.split(",")
+            filtered_pcd, _ = filtered_pcd.remove_statistical_outlier(int(k), float(ratio))
     print(f"   Points remaining: {len(filtered_pcd.points)}")
     output_path = os.path.join(save_dir, f"{obj_name}.ply")
     o3d.io.write_point_cloud(output_path, filtered_pcd)

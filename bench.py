@@ -278,12 +278,46 @@ def post_stage(a, vol, n_blocks, peak):
         pcd = run("sample_points_uniformly" + tag, lambda: mesh.sample_points_uniformly(n_samples, seed=0), points=n_samples)
         flt = run("z_mask" + tag, lambda: zfilter(pcd), lambda r: 48 * n_samples + 48 * len(r.points))
         out["z_mask" + tag]["kept"] = int(len(flt.points))
-        n = len(flt.points)
-        ds = run("voxel_down_sample" + tag, lambda: flt.voxel_down_sample(0.01), lambda r: 36 * (n + len(r.points)), voxel_m=0.01)
+        # the script's own chain filters what survives the z mask; the "_1M" legs feed the filters the full 1 M-point cloud
+        # (the config-5 object size) so that their GB/s figures are measured at the stated size
+        src = flt if not tag else pcd
+        n = len(src.points)
+        ds = run("voxel_down_sample" + tag, lambda: src.voxel_down_sample(0.01), lambda r: 36 * (n + len(r.points)), voxel_m=0.01)
         out["voxel_down_sample" + tag].update(points_in=n, points_out=int(len(ds.points)))
-        sel = run("remove_statistical_outlier" + tag, lambda: flt.remove_statistical_outlier(20, 2.0),
+        sel = run("remove_statistical_outlier" + tag, lambda: src.remove_statistical_outlier(20, 2.0),
                   lambda r: 24 * n * 2 + 8 * n + 36 * len(r[1]), nb_neighbors=20, std_ratio=2.0)
         out["remove_statistical_outlier" + tag].update(points_in=n, kept=int(len(sel[1])))
+
+    # the same chain with the cloud resident in HBM between the operators (otslam_b200.cloud.DeviceCloud: the C-ABI operators
+    # take device pointers); one download at the end.  wall_ms covers the whole chain incl. that download.
+    from otslam_b200.cloud import DeviceCloud
+    import torch
+
+    def chain(n_samples, zmin):
+        dc = DeviceCloud.sample_mesh(vol, n_samples, 0, colors=True)
+        if zmin is not None:
+            dc = dc.zfilter(zmin)
+        dv = dc.voxel_down_sample(0.01)
+        dsor, _ = dv.remove_statistical_outlier(20, 2.0)
+        return dsor.to_pointcloud(), len(dc), len(dv)
+
+    def host_chain(n_samples, zmin):
+        pc = mesh.sample_points_uniformly(n_samples, seed=0)
+        if zmin is not None:
+            pc = zfilter(pc, zmin)
+        hv = pc.voxel_down_sample(0.01)
+        hs, _ = hv.remove_statistical_outlier(20, 2.0)
+        return hs, len(pc.points), len(hv.points)
+
+    for tag, n_samples, zmin in (("", 100000, 0.03), ("_1M", 1000000, None)):
+        for name, fn in (("device_resident", chain), ("host_arrays", host_chain)):
+            fn(n_samples, zmin)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            res, n_in, n_vds = fn(n_samples, zmin)
+            torch.cuda.synchronize()
+            out[f"chain_sample_mask_vds_sor{tag}:{name}"] = {"wall_ms": 1e3 * (time.perf_counter() - t0), "points_sampled": n_samples,
+                                                            "points_after_mask": n_in, "after_vds": n_vds, "kept": int(len(res.points))}
     # reconstruct_rgbd.py writes the mesh instead: the one-off download of the resident arrays
     t0 = time.perf_counter()
     mesh._materialize()

@@ -329,7 +329,7 @@ static int compact_two_pass(int64_t n_items, cudaStream_t s, int64_t* n_out, Dev
     OT_CUDA(base.alloc(n_cta + 1));
     OT_TRY(launch(n_cta, (const int64_t*)nullptr, counts.p));
     OT_TRY(device_exclusive_scan(counts.p, base.p, n_cta, s));
-    OT_CUDA(cudaMemcpyAsync(n_out, base.p + n_cta, 8, cudaMemcpyDeviceToHost, s));
+    OT_CUDA(cudaMemcpyAsync(n_out, base.p + n_cta, 8, cudaMemcpyDefault, s));
     OT_CUDA(cudaStreamSynchronize(s));
     return OTSLAM_OK;
 }
@@ -353,8 +353,8 @@ int otslam_backproject_rgbd(const float* depth_m, const uint8_t* rgb, int width,
     DevBuf<float> dd;
     DevBuf<uint8_t> dc;
     OT_CUDA(dd.alloc(n));
-    OT_CUDA(cudaMemcpy(dd.p, depth_m, n * 4, cudaMemcpyHostToDevice));
-    if (rgb) { OT_CUDA(dc.alloc(n * 3)); OT_CUDA(cudaMemcpy(dc.p, rgb, n * 3, cudaMemcpyHostToDevice)); }
+    OT_CUDA(cudaMemcpy(dd.p, depth_m, n * 4, cudaMemcpyDefault));
+    if (rgb) { OT_CUDA(dc.alloc(n * 3)); OT_CUDA(cudaMemcpy(dc.p, rgb, n * 3, cudaMemcpyDefault)); }
     a.depth = dd.p; a.rgb = rgb ? dc.p : nullptr;
     DevBuf<int> counts;
     DevBuf<int64_t> base;
@@ -372,8 +372,8 @@ int otslam_backproject_rgbd(const float* depth_m, const uint8_t* rgb, int width,
     OT_CUDA(dp.alloc(m * 3));
     if (rgb && colors) OT_CUDA(dcol.alloc(m * 3));
     OT_TRY(launch((int)((n + kItemsPerCta - 1) / kItemsPerCta), base.p, nullptr));
-    OT_CUDA(cudaMemcpy(points, dp.p, m * 24, cudaMemcpyDeviceToHost));
-    if (rgb && colors) OT_CUDA(cudaMemcpy(colors, dcol.p, m * 24, cudaMemcpyDeviceToHost));
+    OT_CUDA(cudaMemcpy(points, dp.p, m * 24, cudaMemcpyDefault));
+    if (rgb && colors) OT_CUDA(cudaMemcpy(colors, dcol.p, m * 24, cudaMemcpyDefault));
     return OTSLAM_OK;
 }
 
@@ -386,10 +386,10 @@ int otslam_mesh_vertex_normals(const double* vertices, int64_t n_vertices, const
     DevBuf<double> dv, dn;
     DevBuf<int32_t> df;
     OT_CUDA(dv.alloc(n_vertices * 3)); OT_CUDA(dn.alloc(n_vertices * 3)); OT_CUDA(df.alloc(n_faces * 3));
-    OT_CUDA(cudaMemcpy(dv.p, vertices, n_vertices * 24, cudaMemcpyHostToDevice));
-    if (n_faces) OT_CUDA(cudaMemcpy(df.p, faces, n_faces * 12, cudaMemcpyHostToDevice));
+    OT_CUDA(cudaMemcpy(dv.p, vertices, n_vertices * 24, cudaMemcpyDefault));
+    if (n_faces) OT_CUDA(cudaMemcpy(df.p, faces, n_faces * 12, cudaMemcpyDefault));
     OT_TRY(device_vertex_normals(dv.p, n_vertices, df.p, n_faces, dn.p, 0));
-    OT_CUDA(cudaMemcpy(normals, dn.p, n_vertices * 24, cudaMemcpyDeviceToHost));
+    OT_CUDA(cudaMemcpy(normals, dn.p, n_vertices * 24, cudaMemcpyDefault));
     return OTSLAM_OK;
 }
 
@@ -403,11 +403,11 @@ int otslam_mesh_sample_uniform(const double* vertices, const double* colors, con
     DevBuf<double> dv, dc, dn, area, total, op, oc, on;
     DevBuf<int32_t> df;
     OT_CUDA(dv.alloc(n_vertices * 3)); OT_CUDA(df.alloc(n_faces * 3)); OT_CUDA(area.alloc(n_faces)); OT_CUDA(total.alloc(1));
-    OT_CUDA(cudaMemcpy(dv.p, vertices, n_vertices * 24, cudaMemcpyHostToDevice));
-    OT_CUDA(cudaMemcpy(df.p, faces, n_faces * 12, cudaMemcpyHostToDevice));
+    OT_CUDA(cudaMemcpy(dv.p, vertices, n_vertices * 24, cudaMemcpyDefault));
+    OT_CUDA(cudaMemcpy(df.p, faces, n_faces * 12, cudaMemcpyDefault));
     const bool has_c = colors && out_colors, has_n = normals && out_normals;
-    if (has_c) { OT_CUDA(dc.alloc(n_vertices * 3)); OT_CUDA(cudaMemcpy(dc.p, colors, n_vertices * 24, cudaMemcpyHostToDevice)); OT_CUDA(oc.alloc(n_samples * 3)); }
-    if (has_n) { OT_CUDA(dn.alloc(n_vertices * 3)); OT_CUDA(cudaMemcpy(dn.p, normals, n_vertices * 24, cudaMemcpyHostToDevice)); OT_CUDA(on.alloc(n_samples * 3)); }
+    if (has_c) { OT_CUDA(dc.alloc(n_vertices * 3)); OT_CUDA(cudaMemcpy(dc.p, colors, n_vertices * 24, cudaMemcpyDefault)); OT_CUDA(oc.alloc(n_samples * 3)); }
+    if (has_n) { OT_CUDA(dn.alloc(n_vertices * 3)); OT_CUDA(cudaMemcpy(dn.p, normals, n_vertices * 24, cudaMemcpyDefault)); OT_CUDA(on.alloc(n_samples * 3)); }
     OT_CUDA(op.alloc(n_samples * 3));
     OpTimer timer;
     tri_area_kernel<<<(unsigned)((n_faces + 255) / 256), 256>>>(dv.p, df.p, n_faces, area.p);
@@ -418,9 +418,9 @@ int otslam_mesh_sample_uniform(const double* vertices, const double* colors, con
                                                                area.p, n_samples, seed, op.p, oc.p, on.p);
     OT_LAUNCHED();
     timer.stop();
-    OT_CUDA(cudaMemcpy(out_points, op.p, n_samples * 24, cudaMemcpyDeviceToHost));
-    if (has_c) OT_CUDA(cudaMemcpy(out_colors, oc.p, n_samples * 24, cudaMemcpyDeviceToHost));
-    if (has_n) OT_CUDA(cudaMemcpy(out_normals, on.p, n_samples * 24, cudaMemcpyDeviceToHost));
+    OT_CUDA(cudaMemcpy(out_points, op.p, n_samples * 24, cudaMemcpyDefault));
+    if (has_c) OT_CUDA(cudaMemcpy(out_colors, oc.p, n_samples * 24, cudaMemcpyDefault));
+    if (has_n) OT_CUDA(cudaMemcpy(out_normals, on.p, n_samples * 24, cudaMemcpyDefault));
     return OTSLAM_OK;
 }
 
@@ -448,9 +448,9 @@ int otslam_volume_mesh_sample(otslam_volume* v, int64_t n_samples, uint64_t seed
                                                                           n_samples, seed, op.p, oc.p, on.p);
         OT_LAUNCHED();
     }
-    OT_CUDA(cudaMemcpyAsync(out_points, op.p, n_samples * 24, cudaMemcpyDeviceToHost, s));
-    if (out_colors) OT_CUDA(cudaMemcpyAsync(out_colors, oc.p, n_samples * 24, cudaMemcpyDeviceToHost, s));
-    if (out_normals) OT_CUDA(cudaMemcpyAsync(out_normals, on.p, n_samples * 24, cudaMemcpyDeviceToHost, s));
+    OT_CUDA(cudaMemcpyAsync(out_points, op.p, n_samples * 24, cudaMemcpyDefault, s));
+    if (out_colors) OT_CUDA(cudaMemcpyAsync(out_colors, oc.p, n_samples * 24, cudaMemcpyDefault, s));
+    if (out_normals) OT_CUDA(cudaMemcpyAsync(out_normals, on.p, n_samples * 24, cudaMemcpyDefault, s));
     OT_CUDA(cudaStreamSynchronize(s));
     return OTSLAM_OK;
 }
@@ -463,9 +463,9 @@ int otslam_cloud_zfilter(const double* points, const double* colors, int64_t n, 
     OT_TRY(use_device(device));
     DevBuf<double> dp, dc, op, oc;
     OT_CUDA(dp.alloc(n * 3));
-    OT_CUDA(cudaMemcpy(dp.p, points, n * 24, cudaMemcpyHostToDevice));
+    OT_CUDA(cudaMemcpy(dp.p, points, n * 24, cudaMemcpyDefault));
     const bool has_c = colors && out_colors;
-    if (has_c) { OT_CUDA(dc.alloc(n * 3)); OT_CUDA(cudaMemcpy(dc.p, colors, n * 24, cudaMemcpyHostToDevice)); }
+    if (has_c) { OT_CUDA(dc.alloc(n * 3)); OT_CUDA(cudaMemcpy(dc.p, colors, n * 24, cudaMemcpyDefault)); }
     DevBuf<int> counts;
     DevBuf<int64_t> base;
     cudaStream_t s = 0;
@@ -483,8 +483,8 @@ int otslam_cloud_zfilter(const double* points, const double* colors, int64_t n, 
     if (has_c) OT_CUDA(oc.alloc(m * 3));
     OT_TRY(launch((int)((n + kItemsPerCta - 1) / kItemsPerCta), base.p, nullptr));
     timer.stop();
-    OT_CUDA(cudaMemcpy(out_points, op.p, m * 24, cudaMemcpyDeviceToHost));
-    if (has_c) OT_CUDA(cudaMemcpy(out_colors, oc.p, m * 24, cudaMemcpyDeviceToHost));
+    OT_CUDA(cudaMemcpy(out_points, op.p, m * 24, cudaMemcpyDefault));
+    if (has_c) OT_CUDA(cudaMemcpy(out_colors, oc.p, m * 24, cudaMemcpyDefault));
     return OTSLAM_OK;
 }
 
@@ -495,7 +495,7 @@ int otslam_grid_to_points(const uint8_t* gray, int width, int height, double res
     const int64_t n = (int64_t)width * height;
     DevBuf<uint8_t> di;
     OT_CUDA(di.alloc(n));
-    OT_CUDA(cudaMemcpy(di.p, gray, n, cudaMemcpyHostToDevice));
+    OT_CUDA(cudaMemcpy(di.p, gray, n, cudaMemcpyDefault));
     DevBuf<int> counts;
     DevBuf<int64_t> base;
     DevBuf<double> op;
@@ -513,7 +513,7 @@ int otslam_grid_to_points(const uint8_t* gray, int width, int height, double res
     OT_CUDA(op.alloc(m * 3));
     OT_TRY(launch((int)((n + kItemsPerCta - 1) / kItemsPerCta), base.p, nullptr));
     timer.stop();
-    OT_CUDA(cudaMemcpy(out_points, op.p, m * 24, cudaMemcpyDeviceToHost));
+    OT_CUDA(cudaMemcpy(out_points, op.p, m * 24, cudaMemcpyDefault));
     return OTSLAM_OK;
 }
 
@@ -524,15 +524,15 @@ static int rigid_apply(const double* points, const double* normals, int64_t n, c
     OT_TRY(use_device(device));
     DevBuf<double> dp, dn, op, on;
     OT_CUDA(dp.alloc(n * 3)); OT_CUDA(op.alloc(n * 3));
-    OT_CUDA(cudaMemcpy(dp.p, points, n * 24, cudaMemcpyHostToDevice));
+    OT_CUDA(cudaMemcpy(dp.p, points, n * 24, cudaMemcpyDefault));
     const bool has_n = normals && out_normals;
-    if (has_n) { OT_CUDA(dn.alloc(n * 3)); OT_CUDA(on.alloc(n * 3)); OT_CUDA(cudaMemcpy(dn.p, normals, n * 24, cudaMemcpyHostToDevice)); }
+    if (has_n) { OT_CUDA(dn.alloc(n * 3)); OT_CUDA(on.alloc(n * 3)); OT_CUDA(cudaMemcpy(dn.p, normals, n * 24, cudaMemcpyDefault)); }
     OpTimer timer;
     rigid_kernel<<<(unsigned)((n + 255) / 256), 256>>>(dp.p, has_n ? dn.p : nullptr, n, a, op.p, has_n ? on.p : nullptr);
     OT_LAUNCHED();
     timer.stop();
-    OT_CUDA(cudaMemcpy(out_points, op.p, n * 24, cudaMemcpyDeviceToHost));
-    if (has_n) OT_CUDA(cudaMemcpy(out_normals, on.p, n * 24, cudaMemcpyDeviceToHost));
+    OT_CUDA(cudaMemcpy(out_points, op.p, n * 24, cudaMemcpyDefault));
+    if (has_n) OT_CUDA(cudaMemcpy(out_normals, on.p, n * 24, cudaMemcpyDefault));
     return OTSLAM_OK;
 }
 
@@ -563,7 +563,7 @@ int otslam_cloud_center(const double* points, int64_t n, double center[3], int d
     OT_TRY(use_device(device));
     DevBuf<double> dp, ax, tot;
     OT_CUDA(dp.alloc(n * 3)); OT_CUDA(ax.alloc(n)); OT_CUDA(tot.alloc(3));
-    OT_CUDA(cudaMemcpy(dp.p, points, n * 24, cudaMemcpyHostToDevice));
+    OT_CUDA(cudaMemcpy(dp.p, points, n * 24, cudaMemcpyDefault));
     OpTimer timer;
     for (int a = 0; a < 3; ++a) {     // coordinates may be negative: the exact chain replays such chunks scalar-wise, still in index order
         axis_extract_kernel<<<(unsigned)((n + 255) / 256), 256>>>(dp.p, n, a, ax.p);
@@ -572,7 +572,7 @@ int otslam_cloud_center(const double* points, int64_t n, double center[3], int d
     }
     timer.stop();
     double h[3];
-    OT_CUDA(cudaMemcpy(h, tot.p, 24, cudaMemcpyDeviceToHost));
+    OT_CUDA(cudaMemcpy(h, tot.p, 24, cudaMemcpyDefault));
     for (int a = 0; a < 3; ++a) center[a] = h[a] / (double)n;
     return OTSLAM_OK;
 }
@@ -585,13 +585,13 @@ int otslam_grid_smart_paste(uint8_t* base, const uint8_t* overlay, int width, in
     const size_t n = (size_t)width * height;
     DevBuf<uint8_t> db, dov;
     OT_CUDA(db.alloc(n)); OT_CUDA(dov.alloc(n));
-    OT_CUDA(cudaMemcpy(db.p, base, n, cudaMemcpyHostToDevice));
-    OT_CUDA(cudaMemcpy(dov.p, overlay, n, cudaMemcpyHostToDevice));
+    OT_CUDA(cudaMemcpy(db.p, base, n, cudaMemcpyDefault));
+    OT_CUDA(cudaMemcpy(dov.p, overlay, n, cudaMemcpyDefault));
     OpTimer timer;
     smart_paste_kernel<<<(unsigned)(((int64_t)w * h + 255) / 256), 256>>>(db.p, dov.p, width, x, y, w, h, unknown_pixel, threshold);
     OT_LAUNCHED();
     timer.stop();
-    OT_CUDA(cudaMemcpy(base, db.p, n, cudaMemcpyDeviceToHost));
+    OT_CUDA(cudaMemcpy(base, db.p, n, cudaMemcpyDefault));
     return OTSLAM_OK;
 }
 
@@ -614,11 +614,11 @@ int otslam_cloud_merge_pack(int n_clouds, const double* const* points, const dou
     for (int i = 0; i < n_clouds; ++i) {
         if (counts[i] == 0) continue;
         OT_CUDA(dp[i].alloc(counts[i] * 3));
-        OT_CUDA(cudaMemcpyAsync(dp[i].p, points[i], counts[i] * 24, cudaMemcpyHostToDevice, s));
+        OT_CUDA(cudaMemcpyAsync(dp[i].p, points[i], counts[i] * 24, cudaMemcpyDefault, s));
         hp[i] = dp[i].p;
         if (!paint && colors && colors[i]) {
             OT_CUDA(dc[i].alloc(counts[i] * 3));
-            OT_CUDA(cudaMemcpyAsync(dc[i].p, colors[i], counts[i] * 24, cudaMemcpyHostToDevice, s));
+            OT_CUDA(cudaMemcpyAsync(dc[i].p, colors[i], counts[i] * 24, cudaMemcpyDefault, s));
             hc[i] = dc[i].p;
         }
     }
@@ -626,9 +626,9 @@ int otslam_cloud_merge_pack(int n_clouds, const double* const* points, const dou
     DevBuf<int64_t> doff;
     DevBuf<uint8_t> dpaint, dout;
     OT_CUDA(dpp.alloc(n_clouds)); OT_CUDA(dcp.alloc(n_clouds)); OT_CUDA(doff.alloc(n_clouds + 1)); OT_CUDA(dout.alloc(total * 27));
-    OT_CUDA(cudaMemcpyAsync(dpp.p, hp.data(), n_clouds * sizeof(double*), cudaMemcpyHostToDevice, s));
-    OT_CUDA(cudaMemcpyAsync(dcp.p, hc.data(), n_clouds * sizeof(double*), cudaMemcpyHostToDevice, s));
-    OT_CUDA(cudaMemcpyAsync(doff.p, off.data(), (n_clouds + 1) * 8, cudaMemcpyHostToDevice, s));
+    OT_CUDA(cudaMemcpyAsync(dpp.p, hp.data(), n_clouds * sizeof(double*), cudaMemcpyDefault, s));
+    OT_CUDA(cudaMemcpyAsync(dcp.p, hc.data(), n_clouds * sizeof(double*), cudaMemcpyDefault, s));
+    OT_CUDA(cudaMemcpyAsync(doff.p, off.data(), (n_clouds + 1) * 8, cudaMemcpyDefault, s));
     std::vector<uint8_t> pb;
     if (paint) {
         pb.resize(3 * n_clouds);
@@ -637,7 +637,7 @@ int otslam_cloud_merge_pack(int n_clouds, const double* const* points, const dou
             pb[i] = (uint8_t)std::floor(c * 255.0 + 0.5);
         }
         OT_CUDA(dpaint.alloc(3 * n_clouds));
-        OT_CUDA(cudaMemcpyAsync(dpaint.p, pb.data(), 3 * n_clouds, cudaMemcpyHostToDevice, s));
+        OT_CUDA(cudaMemcpyAsync(dpaint.p, pb.data(), 3 * n_clouds, cudaMemcpyDefault, s));
     }
     MergeArgs a;
     a.pts = dpp.p; a.cols = dcp.p; a.offsets = doff.p; a.paint = paint ? dpaint.p : nullptr; a.n_clouds = n_clouds; a.total = total;
@@ -645,7 +645,7 @@ int otslam_cloud_merge_pack(int n_clouds, const double* const* points, const dou
     merge_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(a, dout.p);
     OT_LAUNCHED();
     timer.stop();
-    OT_CUDA(cudaMemcpyAsync(out_records, dout.p, total * 27, cudaMemcpyDeviceToHost, s));
+    OT_CUDA(cudaMemcpyAsync(out_records, dout.p, total * 27, cudaMemcpyDefault, s));
     OT_CUDA(cudaStreamSynchronize(s));
     return OTSLAM_OK;
 }

@@ -62,11 +62,11 @@ static int cloud_minmax(const double* d_pts, int64_t n, double* mn, double* mx) 
     DevBuf<unsigned long long> mm;
     OT_CUDA(mm.alloc(6));
     unsigned long long init[6] = {~0ull, ~0ull, ~0ull, 0, 0, 0};
-    OT_CUDA(cudaMemcpy(mm.p, init, sizeof(init), cudaMemcpyHostToDevice));
+    OT_CUDA(cudaMemcpy(mm.p, init, sizeof(init), cudaMemcpyDefault));
     minmax_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 148 * 8), 256>>>(d_pts, n, mm.p);
     OT_LAUNCHED();
     unsigned long long h[6];
-    OT_CUDA(cudaMemcpy(h, mm.p, sizeof(h), cudaMemcpyDeviceToHost));
+    OT_CUDA(cudaMemcpy(h, mm.p, sizeof(h), cudaMemcpyDefault));
     for (int a = 0; a < 3; ++a) { mn[a] = key2d(h[a]); mx[a] = key2d(h[3 + a]); }
     return OTSLAM_OK;
 }
@@ -245,12 +245,12 @@ static int find_segments(const uint64_t* d_keys, int64_t n, DevBuf<int32_t>& seg
     seg_heads_kernel<<<n_cta, 256>>>(d_keys, n, nullptr, counts.p, nullptr);
     OT_LAUNCHED();
     OT_TRY(device_exclusive_scan(counts.p, base.p, n_cta, 0));
-    OT_CUDA(cudaMemcpy(n_seg, base.p + n_cta, 8, cudaMemcpyDeviceToHost));
+    OT_CUDA(cudaMemcpy(n_seg, base.p + n_cta, 8, cudaMemcpyDefault));
     OT_CUDA(seg_start.alloc(*n_seg + 1));
     seg_heads_kernel<<<n_cta, 256>>>(d_keys, n, base.p, nullptr, seg_start.p);
     OT_LAUNCHED();
     const int32_t nn = (int32_t)n;
-    OT_CUDA(cudaMemcpy(seg_start.p + *n_seg, &nn, 4, cudaMemcpyHostToDevice));
+    OT_CUDA(cudaMemcpy(seg_start.p + *n_seg, &nn, 4, cudaMemcpyDefault));
     return OTSLAM_OK;
 }
 
@@ -643,7 +643,7 @@ static int build_search(const double* d_pts, int64_t n, GridBuffers& bc, GridBuf
     crowding_kernel<<<(unsigned)((bc.n_seg + 255) / 256), 256>>>(bc.seg.p, bc.n_seg, sq.p);
     OT_LAUNCHED();
     unsigned long long hsq = 0;
-    OT_CUDA(cudaMemcpy(&hsq, sq.p, 8, cudaMemcpyDeviceToHost));
+    OT_CUDA(cudaMemcpy(&hsq, sq.p, 8, cudaMemcpyDefault));
     const double occ = (double)hsq / (double)n;
     static const double target = getenv("OTSLAM_KNN_OCC") ? atof(getenv("OTSLAM_KNN_OCC")) : kKnnFineOccupancy;   // dev knobs
     static const int rings = getenv("OTSLAM_KNN_RINGS") ? atoi(getenv("OTSLAM_KNN_RINGS")) : kKnnFineRings;
@@ -711,8 +711,8 @@ int otslam_cloud_voxel_down_sample(const double* points, const double* colors, i
     OT_TRY(use_device(device));
     DevBuf<double> dp, dc;
     OT_CUDA(dp.alloc(n * 3));
-    OT_CUDA(cudaMemcpy(dp.p, points, n * 24, cudaMemcpyHostToDevice));
-    if (colors) { OT_CUDA(dc.alloc(n * 3)); OT_CUDA(cudaMemcpy(dc.p, colors, n * 24, cudaMemcpyHostToDevice)); }
+    OT_CUDA(cudaMemcpy(dp.p, points, n * 24, cudaMemcpyDefault));
+    if (colors) { OT_CUDA(dc.alloc(n * 3)); OT_CUDA(cudaMemcpy(dc.p, colors, n * 24, cudaMemcpyDefault)); }
     OpTimer timer;
     double mn[3], mx[3];
     OT_TRY(cloud_minmax(dp.p, n, mn, mx));
@@ -742,10 +742,10 @@ int otslam_cloud_voxel_down_sample(const double* points, const double* colors, i
     voxel_mean_kernel<<<(unsigned)((m + 127) / 128), 128>>>(dp.p, colors ? dc.p : nullptr, k1.p, i1.p, seg.p, m, L, op.p, oc.p, ok.p, on.p);
     OT_LAUNCHED();
     timer.stop();
-    OT_CUDA(cudaMemcpy(out_points, op.p, m * 24, cudaMemcpyDeviceToHost));
-    if (colors && out_colors) OT_CUDA(cudaMemcpy(out_colors, oc.p, m * 24, cudaMemcpyDeviceToHost));
-    if (out_keys) OT_CUDA(cudaMemcpy(out_keys, ok.p, m * 12, cudaMemcpyDeviceToHost));
-    if (out_counts) OT_CUDA(cudaMemcpy(out_counts, on.p, m * 4, cudaMemcpyDeviceToHost));
+    OT_CUDA(cudaMemcpy(out_points, op.p, m * 24, cudaMemcpyDefault));
+    if (colors && out_colors) OT_CUDA(cudaMemcpy(out_colors, oc.p, m * 24, cudaMemcpyDefault));
+    if (out_keys) OT_CUDA(cudaMemcpy(out_keys, ok.p, m * 12, cudaMemcpyDefault));
+    if (out_counts) OT_CUDA(cudaMemcpy(out_counts, on.p, m * 4, cudaMemcpyDefault));
     return OTSLAM_OK;
 }
 
@@ -763,7 +763,7 @@ int otslam_cloud_remove_statistical_outlier(const double* points, int64_t n, int
     OT_TRY(use_device(device));
     DevBuf<double> dp;
     OT_CUDA(dp.alloc(n * 3));
-    OT_CUDA(cudaMemcpy(dp.p, points, n * 24, cudaMemcpyHostToDevice));
+    OT_CUDA(cudaMemcpy(dp.p, points, n * 24, cudaMemcpyDefault));
     OpTimer timer;
     KnnArgs a;
     GridBuffers bc, bf, bt;
@@ -774,15 +774,15 @@ int otslam_cloud_remove_statistical_outlier(const double* points, int64_t n, int
     a.nq = n; a.mode = 0; a.n = n; a.k = k; a.dbar = dbar.p;
     knn_mean_dist_kernel<<<(unsigned)((n + kKnnWarps - 1) / kKnnWarps), kKnnWarps * 32>>>(a);
     OT_LAUNCHED();
-    if (mean_dist) OT_CUDA(cudaMemcpy(mean_dist, dbar.p, n * 8, cudaMemcpyDeviceToHost));
+    if (mean_dist) OT_CUDA(cudaMemcpy(mean_dist, dbar.p, n * 8, cudaMemcpyDefault));
     // global statistics in sequential index order; scalars finished on the host in FP64
     double sum = 0.0, sq = 0.0;
     OT_TRY(device_ordered_sum(dbar.p, n, 2, nullptr, 0.0, scal.p, 0));
-    OT_CUDA(cudaMemcpy(&sum, scal.p, 8, cudaMemcpyDeviceToHost));
+    OT_CUDA(cudaMemcpy(&sum, scal.p, 8, cudaMemcpyDefault));
     const int64_t valid = n;   // the query point is its own first neighbour, so every point has >= 1
     const double mean = sum / (double)valid;
     OT_TRY(device_ordered_sum(dbar.p, n, 3, nullptr, mean, scal.p, 0));
-    OT_CUDA(cudaMemcpy(&sq, scal.p, 8, cudaMemcpyDeviceToHost));
+    OT_CUDA(cudaMemcpy(&sq, scal.p, 8, cudaMemcpyDefault));
     const double sd = valid > 1 ? std::sqrt(sq / (double)(valid - 1)) : 0.0;
     const double thr = mean + std_ratio * sd;
     const int n_cta = (int)((n + 1023) / 1024);
@@ -793,14 +793,14 @@ int otslam_cloud_remove_statistical_outlier(const double* points, int64_t n, int
     OT_LAUNCHED();
     OT_TRY(device_exclusive_scan(counts.p, base.p, n_cta, 0));
     int64_t m = 0;
-    OT_CUDA(cudaMemcpy(&m, base.p + n_cta, 8, cudaMemcpyDeviceToHost));
+    OT_CUDA(cudaMemcpy(&m, base.p + n_cta, 8, cudaMemcpyDefault));
     *n_out = m;
     if (m == 0) return OTSLAM_OK;
     OT_CUDA(oidx.alloc(m));
     sor_select_kernel<<<n_cta, 256>>>(dbar.p, n, thr, base.p, nullptr, oidx.p);
     OT_LAUNCHED();
     timer.stop();
-    OT_CUDA(cudaMemcpy(out_indices, oidx.p, m * 8, cudaMemcpyDeviceToHost));
+    OT_CUDA(cudaMemcpy(out_indices, oidx.p, m * 8, cudaMemcpyDefault));
     return OTSLAM_OK;
 }
 
@@ -814,8 +814,8 @@ int otslam_cloud_nn_distance(const double* source, int64_t n_source, const doubl
     OT_TRY(use_device(device));
     DevBuf<double> dt, dsrc, dout;
     OT_CUDA(dt.alloc(n_target * 3)); OT_CUDA(dsrc.alloc(n_source * 3)); OT_CUDA(dout.alloc(n_source));
-    OT_CUDA(cudaMemcpy(dt.p, target, n_target * 24, cudaMemcpyHostToDevice));
-    OT_CUDA(cudaMemcpy(dsrc.p, source, n_source * 24, cudaMemcpyHostToDevice));
+    OT_CUDA(cudaMemcpy(dt.p, target, n_target * 24, cudaMemcpyDefault));
+    OT_CUDA(cudaMemcpy(dsrc.p, source, n_source * 24, cudaMemcpyDefault));
     OpTimer timer;
     KnnArgs a;
     GridBuffers bc, bf, bt;
@@ -824,7 +824,7 @@ int otslam_cloud_nn_distance(const double* source, int64_t n_source, const doubl
     knn_mean_dist_kernel<<<(unsigned)((n_source + kKnnWarps - 1) / kKnnWarps), kKnnWarps * 32>>>(a);
     OT_LAUNCHED();
     timer.stop();
-    OT_CUDA(cudaMemcpy(out_dist, dout.p, n_source * 8, cudaMemcpyDeviceToHost));
+    OT_CUDA(cudaMemcpy(out_dist, dout.p, n_source * 8, cudaMemcpyDefault));
     return OTSLAM_OK;
 }
 

@@ -290,6 +290,13 @@ class PointCloud:
         r._points = np.ascontiguousarray(op[:m.value])
         if oc is not None:
             r._colors = np.ascontiguousarray(oc[:m.value])
+        if self.has_normals():
+            # Open3D averages normals per voxel exactly like colours (sum in point-index order / count, not re-normalised):
+            # the same kernel with the normals in the colour slot gives the same voxels in the same order
+            on = np.empty((n, 3), np.float64)
+            _lib.check(_lib.lib.otslam_cloud_voxel_down_sample(_lib.ptr(self._points), _lib.ptr(self._normals), n, float(voxel_size),
+                                                               _lib.ptr(op), _lib.ptr(on), None, None, C.byref(m), 0))
+            r._normals = np.ascontiguousarray(on[:m.value])
         return r
 
     def remove_statistical_outlier(self, nb_neighbors, std_ratio, print_progress=False):

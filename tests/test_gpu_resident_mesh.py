@@ -65,3 +65,37 @@ def test_lazy_mesh_survives_reextract_and_reset():
     assert len(e.vertices) == 0 and not e.has_triangles()
     with pytest.raises(RuntimeError):
         e.sample_points_uniformly(10)
+
+
+def test_device_cloud_chain_equals_host_chain():
+    """sample -> z mask -> voxel_down_sample -> remove_statistical_outlier on CUDA tensors (otslam_b200.cloud.DeviceCloud: the
+    operators take device pointers, nothing crosses PCIe between them) == the same chain through host arrays, bit for bit."""
+    from otslam_b200.cloud import DeviceCloud
+    o3d, vol = _volume()
+    mesh = vol.extract_triangle_mesh()
+    mesh.compute_vertex_normals()
+    host = mesh.sample_points_uniformly(60000, seed=9)
+    pts, cols = np.asarray(host.points), np.asarray(host.colors)
+    keep = pts[:, 2] >= 0.03
+    hf = o3d.geometry.PointCloud()
+    hf.points, hf.colors = pts[keep], cols[keep]
+    hv = hf.voxel_down_sample(0.012)
+    hs, hidx = hv.remove_statistical_outlier(20, 2.0)
+    dc = DeviceCloud.sample_mesh(vol._vol, 60000, 9, colors=True, normals=True)
+    assert dc.points.is_cuda and (dc.points.cpu().numpy() == pts).all() and (dc.normals.cpu().numpy() == np.asarray(host.normals)).all()
+    df = dc.zfilter(0.03)
+    assert len(df) == int(keep.sum()) and (df.points.cpu().numpy() == pts[keep]).all() and (df.colors.cpu().numpy() == cols[keep]).all()
+    dv = df.voxel_down_sample(0.012)
+    assert len(dv) == len(hv.points) and (dv.points.cpu().numpy() == hv.points).all() and (dv.colors.cpu().numpy() == hv.colors).all()
+    ds, didx = dv.remove_statistical_outlier(20, 2.0)
+    assert didx.is_cuda and didx.cpu().tolist() == hidx
+    out = ds.to_pointcloud()
+    assert (out.points == hs.points).all() and (out.colors == hs.colors).all() and 0 < len(out.points) < len(hv.points)
+    # voxel_down_sample averages normals like colours (ADVICE r1): host compat and device chain agree, and a unit-normal
+    # input gives means of length <= 1
+    hn = o3d.geometry.PointCloud()
+    hn.points, hn.colors, hn.normals = pts, cols, np.asarray(host.normals)
+    hnv = hn.voxel_down_sample(0.012)
+    dnv = dc.voxel_down_sample(0.012)
+    assert hnv.has_normals() and (dnv.normals.cpu().numpy() == hnv.normals).all() and (dnv.points.cpu().numpy() == hnv.points).all()
+    assert np.linalg.norm(hnv.normals, axis=1).max() <= 1 + 1e-12
