@@ -366,7 +366,7 @@ def hybrid_merge_stage(peak, n_obj=20, per_obj=1_000_000, map_px=2000):
     return out
 
 
-def files_e2e(a, seq, n_files=512):
+def files_e2e(a, seq, n_files=768):
     """The drop-in script's loop as a user runs it: a capture tree on disk (color/*.jpg, depth/*.png, poses/*.txt as
     scanner_node.cpp writes them) -> pipeline.integrate_files (thread-pool decode one chunk ahead of the GPU) into
     a fresh ScalableTSDFVolume.  File decoding, not the GPU, bounds this number; the sequential decode rate is what

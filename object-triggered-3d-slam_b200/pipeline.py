@@ -35,7 +35,14 @@ def load_frame(color_path, depth_path, pose_path, intrinsics, T_fix):
 
 
 def _decode_workers():
-    return max(1, min(16, int(os.environ.get("OTSLAM_DECODE_THREADS", "0")) or (os.cpu_count() or 1)))
+    n = int(os.environ.get("OTSLAM_DECODE_THREADS", "0"))
+    if n > 0:
+        return min(n, 64)
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        cores = os.cpu_count() or 1
+    return max(1, min(32 if sidecar_enabled() else 16, cores))      # side-car reads are I/O + memcpy (GIL released): more threads pay
 
 
 def read_pose(path):
