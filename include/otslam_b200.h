@@ -175,7 +175,10 @@ int otslam_volume_points_copy(otslam_volume* v, double* points, double* colors, 
  * TSDF at every point of the last extraction (Open3D GetNormalAt / GetTSDFAt); normals [n][3], host or device */
 int otslam_volume_points_normals(otslam_volume* v, double* normals);
 
-/* ---- stateless image / cloud operators (host in, host out) */
+/* ---- stateless image / cloud operators.  Every pointer argument may be a HOST pointer or a DEVICE pointer of `device`
+ *      (unified addressing; the copies inside become device-to-device): a caller that keeps its clouds in HBM between
+ *      operators (otslam_b200/cloud.py: DeviceCloud) never crosses PCIe.  Device inputs must be complete (producer stream
+ *      synchronised); results are complete on return. */
 /* RGBDImage.create_from_color_and_depth depth half (reconstruct_rgbd.py:99-104) */
 int otslam_depth_convert(const uint16_t* depth, int64_t n, double depth_scale, double depth_trunc, float* out,
                          int device);
@@ -207,6 +210,12 @@ int otslam_cloud_remove_statistical_outlier(const double* points, int64_t n, int
  * (eval/eval_table_chair/eval_table_chair.py:106-119; SURVEY 8f "next" row 3) */
 int otslam_cloud_nn_distance(const double* source, int64_t n_source, const double* target, int64_t n_target,
                              double* out_dist, int device);
+/* correspondence search of o3d.pipelines.registration.registration_icp (eval/eval_table_chair/eval_table_chair.py:90-104):
+ * for every source point the index of the nearest target point strictly closer than `radius`, or -1; out_dist2 (nullable)
+ * = the squared distance.  The ICP loop around it (Umeyama update, convergence test) is host code in
+ * o3d_compat/pipelines.py. */
+int otslam_cloud_nn_within(const double* source, int64_t n_source, const double* target, int64_t n_target, double radius,
+                           int32_t* out_index, double* out_dist2, int device);
 /* create_map_cloud's pixel loop (fusion/hybrid_map.py:45-55); out sized w*h*3 (or NULL to count) */
 int otslam_grid_to_points(const uint8_t* gray, int width, int height, double resolution, double origin_x,
                           double origin_y, int threshold, double* out_points, int64_t* n_out, int device);

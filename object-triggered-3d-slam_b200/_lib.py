@@ -74,6 +74,7 @@ _SIGS = {
     "otslam_cloud_voxel_down_sample": (_i, [_vp, _vp, _i64, _d, _vp, _vp, _vp, _vp, C.POINTER(_i64), _i]),
     "otslam_cloud_remove_statistical_outlier": (_i, [_vp, _i64, _i, _d, _vp, C.POINTER(_i64), _vp, _i]),
     "otslam_cloud_nn_distance": (_i, [_vp, _i64, _vp, _i64, _vp, _i]),
+    "otslam_cloud_nn_within": (_i, [_vp, _i64, _vp, _i64, _d, _vp, _vp, _i]),
     "otslam_grid_to_points": (_i, [_vp, _i, _i, _d, _d, _d, _i, _vp, C.POINTER(_i64), _i]),
     "otslam_cloud_transform": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _i]),
     "otslam_cloud_center": (_i, [_vp, _i64, _vp, _i]),

@@ -804,6 +804,83 @@ int otslam_cloud_remove_statistical_outlier(const double* points, int64_t n, int
     return OTSLAM_OK;
 }
 
+// ---- correspondence search of point-to-point ICP (o3d.pipelines.registration.registration_icp,
+// /root/reference/eval/eval_table_chair/eval_table_chair.py:90-104): for every source point the nearest target point
+// strictly closer than `radius` (KDTree SearchHybrid(point, radius, 1)), or -1.  The radius bounds the search, so a uniform
+// grid with cell = radius needs the 27 cells around the query only: one thread per query, exact FP64 squared distances in
+// the (dx^2 + dy^2) + dz^2 order, ties broken towards the lower target index (deterministic).
+__global__ void __launch_bounds__(128) nn_within_kernel(KnnGrid g, const double* __restrict__ pts, const double* __restrict__ qpts,
+                                                        int64_t nq, double r2, int32_t* __restrict__ out_idx, double* __restrict__ out_d2) {
+    const int64_t qi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= nq) return;
+    const double q[3] = {qpts[3 * qi], qpts[3 * qi + 1], qpts[3 * qi + 2]};
+    int c[3];
+#pragma unroll
+    for (int ax = 0; ax < 3; ++ax)      // may lie outside the grid: clamp to one cell beyond it (still "no cell in range")
+        c[ax] = (int)fmin(fmax(floor(__ddiv_rn(__dsub_rn(q[ax], g.mn[ax]), g.cell)), -2.0), (double)g.dim[ax] + 1.0);
+    double best = r2;
+    int bi = -1;
+    for (int dz = -1; dz <= 1; ++dz)
+        for (int dy = -1; dy <= 1; ++dy)
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int x = c[0] + dx, y = c[1] + dy, z = c[2] + dz;
+                if (x < 0 || x >= g.dim[0] || y < 0 || y >= g.dim[1] || z < 0 || z >= g.dim[2]) continue;
+                const uint64_t key = layout_key(g.L, x, y, z);
+                uint32_t h = hash_key(key) & g.cap_mask;
+                int seg = -1;
+                for (;;) {
+                    const uint64_t hk = g.hkeys[h];
+                    if (hk == key) { seg = g.hvals[h]; break; }
+                    if (hk == kEmptyKey) break;
+                    h = (h + 1) & g.cap_mask;
+                }
+                if (seg < 0) continue;
+                for (int j = g.seg_start[seg]; j < g.seg_start[seg + 1]; ++j) {
+                    const int pi = g.idx[j];
+                    const double ex = __dsub_rn(q[0], pts[3 * (size_t)pi]), ey = __dsub_rn(q[1], pts[3 * (size_t)pi + 1]),
+                                 ez = __dsub_rn(q[2], pts[3 * (size_t)pi + 2]);
+                    const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
+                    if (d2 < best || (d2 == best && bi >= 0 && pi < bi)) { best = d2; bi = pi; }
+                }
+            }
+    out_idx[qi] = bi;
+    if (out_d2) out_d2[qi] = bi >= 0 ? best : -1.0;
+}
+
+int otslam_cloud_nn_within(const double* source, int64_t n_source, const double* target, int64_t n_target, double radius,
+                           int32_t* out_index, double* out_dist2, int device) {
+    if (n_source < 0 || n_target < 0 || (n_source && (!source || !out_index)) || (n_target && !target) || !(radius > 0.0))
+        return set_error(OTSLAM_ERR_INVALID, "bad arguments");
+    if (n_source == 0) return OTSLAM_OK;
+    if (n_target > 0x7fffffffLL || n_source > 0x7fffffffLL) return set_error(OTSLAM_ERR_OVERFLOW, "more than 2^31 points");
+    OT_TRY(use_device(device));
+    DevBuf<double> dt, dsrc, dd2;
+    DevBuf<int32_t> di;
+    OT_CUDA(dsrc.alloc(n_source * 3)); OT_CUDA(di.alloc(n_source)); OT_CUDA(dd2.alloc(n_source));
+    OT_CUDA(cudaMemcpy(dsrc.p, source, n_source * 24, cudaMemcpyDefault));
+    if (n_target == 0) {
+        OT_CUDA(cudaMemset(di.p, 0xFF, (size_t)n_source * 4));
+    } else {
+        OT_CUDA(dt.alloc(n_target * 3));
+        OT_CUDA(cudaMemcpy(dt.p, target, n_target * 24, cudaMemcpyDefault));
+        OpTimer timer;
+        double mn[3], mx[3];
+        OT_TRY(cloud_minmax(dt.p, n_target, mn, mx));
+        GridBuffers b;
+        KnnGrid g;
+        OT_TRY(build_grid(dt.p, n_target, mn, mx, radius, 1 << 20, b, g));
+        // build_grid may have enlarged the cell (never shrinks it): 27 cells of size >= radius still cover the ball
+        nn_within_kernel<<<(unsigned)((n_source + 127) / 128), 128>>>(g, dt.p, dsrc.p, n_source, radius * radius, di.p, dd2.p);
+        OT_LAUNCHED();
+        timer.stop();
+        OT_CUDA(cudaDeviceSynchronize());
+    }
+    OT_CUDA(cudaMemcpy(out_index, di.p, n_source * 4, cudaMemcpyDefault));
+    if (out_dist2 && n_target) OT_CUDA(cudaMemcpy(out_dist2, dd2.p, n_source * 8, cudaMemcpyDefault));
+    OT_CUDA(cudaDeviceSynchronize());
+    return OTSLAM_OK;
+}
+
 int otslam_cloud_nn_distance(const double* source, int64_t n_source, const double* target, int64_t n_target, double* out_dist,
                              int device) {
     if (n_source < 0 || n_target < 0 || (n_source && (!source || !out_dist)) || (n_target && !target))

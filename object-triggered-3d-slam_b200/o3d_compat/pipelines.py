@@ -87,3 +87,115 @@ class ScalableTSDFVolume:
 
 
 integration = types.SimpleNamespace(ScalableTSDFVolume=ScalableTSDFVolume, TSDFVolumeColorType=TSDFVolumeColorType)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# o3d.pipelines.registration: point-to-point ICP as the reference's evaluation scripts call it
+# (/root/reference/eval/eval_table_chair/eval_table_chair.py:90-104).  Correspondence search and the rigid
+# update of the source run on the GPU (otslam_cloud_nn_within, otslam_cloud_transform); the 3x3 SVD of the Umeyama step
+# and the convergence test are host arithmetic, as in Open3D.
+# ---------------------------------------------------------------------------------------------------------------------
+class TransformationEstimationPointToPoint:
+    def __init__(self, with_scaling=False):
+        if with_scaling:
+            raise RuntimeError("TransformationEstimationPointToPoint(with_scaling=True) is not supported")
+        self.with_scaling = False
+
+    @staticmethod
+    def compute_transformation(src, dst):
+        """Eigen::umeyama(src, dst, false): least-squares rigid transform src -> dst."""
+        ms, md = src.mean(axis=0), dst.mean(axis=0)
+        cov = (dst - md).T @ (src - ms) / len(src)
+        U, _, Vt = np.linalg.svd(cov)
+        S = np.eye(3)
+        if np.linalg.det(U) * np.linalg.det(Vt) < 0:
+            S[2, 2] = -1.0
+        T = np.eye(4)
+        T[:3, :3] = U @ S @ Vt
+        T[:3, 3] = md - T[:3, :3] @ ms
+        return T
+
+
+class ICPConvergenceCriteria:
+    def __init__(self, relative_fitness=1e-6, relative_rmse=1e-6, max_iteration=30):
+        self.relative_fitness, self.relative_rmse, self.max_iteration = float(relative_fitness), float(relative_rmse), int(max_iteration)
+
+
+class RegistrationResult:
+    def __init__(self):
+        self.transformation = np.eye(4)
+        self.fitness, self.inlier_rmse = 0.0, 0.0
+        self.correspondence_set = np.zeros((0, 2), np.int32)
+
+    def __repr__(self):
+        return (f"RegistrationResult with fitness={self.fitness:e}, inlier_rmse={self.inlier_rmse:e}, and "
+                f"correspondence_set size of {len(self.correspondence_set)}")
+
+
+def _correspondences(src_pts, tgt_pts, max_dist):
+    n = len(src_pts)
+    idx = np.empty(n, np.int32)
+    d2 = np.empty(n, np.float64)
+    _lib.check(_lib.lib.otslam_cloud_nn_within(_lib.ptr(src_pts), n, _lib.ptr(tgt_pts), len(tgt_pts), float(max_dist), _lib.ptr(idx),
+                                               _lib.ptr(d2), 0))
+    sel = np.nonzero(idx >= 0)[0]
+    return sel, idx[sel], d2[sel]
+
+
+def evaluate_registration(source, target, max_correspondence_distance, transformation=None):
+    """o3d.pipelines.registration.evaluate_registration: fitness = inliers / |source|, inlier_rmse over the inliers."""
+    src = geometry.PointCloud(np.asarray(source.points))
+    if transformation is not None:
+        src.transform(transformation)
+    r = RegistrationResult()
+    r.transformation = np.eye(4) if transformation is None else np.array(transformation, np.float64)
+    tgt = np.ascontiguousarray(np.asarray(target.points), np.float64)
+    sel, ti, d2 = _correspondences(np.ascontiguousarray(src.points), tgt, max_correspondence_distance)
+    if len(sel):
+        r.fitness = len(sel) / len(src.points)
+        r.inlier_rmse = float(np.sqrt(d2.sum() / len(sel)))
+        r.correspondence_set = np.stack([sel.astype(np.int32), ti.astype(np.int32)], 1)
+    return r
+
+
+def registration_icp(source, target, max_correspondence_distance, init=None, estimation_method=None, criteria=None):
+    """registration_icp(source, target, threshold, init, TransformationEstimationPointToPoint(), ICPConvergenceCriteria(...))."""
+    estimation_method = estimation_method or TransformationEstimationPointToPoint()
+    criteria = criteria or ICPConvergenceCriteria()
+    if not isinstance(estimation_method, TransformationEstimationPointToPoint):
+        raise RuntimeError("only TransformationEstimationPointToPoint is supported")
+    if max_correspondence_distance <= 0:
+        raise RuntimeError("[RegistrationICP] Invalid max_correspondence_distance.")
+    T = np.eye(4) if init is None else np.array(init, np.float64)
+    tgt = np.ascontiguousarray(np.asarray(target.points), np.float64)
+    pcd = geometry.PointCloud(np.asarray(source.points))
+    pcd.transform(T)
+
+    def evaluate():
+        r = RegistrationResult()
+        sel, ti, d2 = _correspondences(np.ascontiguousarray(pcd.points), tgt, max_correspondence_distance)
+        if len(sel):
+            r.fitness = len(sel) / len(pcd.points)
+            r.inlier_rmse = float(np.sqrt(d2.sum() / len(sel)))
+            r.correspondence_set = np.stack([sel.astype(np.int32), ti.astype(np.int32)], 1)
+        return r
+
+    result = evaluate()
+    for _ in range(criteria.max_iteration):
+        if len(result.correspondence_set) < 3:
+            break
+        cs = result.correspondence_set
+        update = estimation_method.compute_transformation(np.asarray(pcd.points)[cs[:, 0]], tgt[cs[:, 1]])
+        T = update @ T
+        pcd.transform(update)
+        backup, result = result, evaluate()
+        if abs(backup.fitness - result.fitness) < criteria.relative_fitness and \
+                abs(backup.inlier_rmse - result.inlier_rmse) < criteria.relative_rmse:
+            break
+    result.transformation = T
+    return result
+
+
+registration = types.SimpleNamespace(registration_icp=registration_icp, evaluate_registration=evaluate_registration,
+                                     TransformationEstimationPointToPoint=TransformationEstimationPointToPoint,
+                                     ICPConvergenceCriteria=ICPConvergenceCriteria, RegistrationResult=RegistrationResult)

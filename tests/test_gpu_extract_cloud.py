@@ -249,3 +249,40 @@ def test_scratch_cache_and_operator_timer():
     assert (np.asarray(a.points) == np.asarray(b.points)).all()
     want, _, _, _ = oracle.voxel_down_sample(np.asarray(pc.points), None, 0.05)
     assert (np.asarray(b.points) == want).all()
+
+
+def test_icp_point_to_point_recovers_a_known_motion(mesh):
+    """o3d.pipelines.registration.registration_icp as eval_table_chair.py:90-104 calls it (point-to-point, identity init,
+    max_iteration=2000): correspondences (otslam_cloud_nn_within) equal a cKDTree radius-bounded nearest-neighbour search,
+    and ICP undoes a small known rigid motion of the cloud."""
+    import otslam_b200.o3d_compat as o3d
+    from otslam_b200 import _lib
+    v, col, f, nrm = mesh
+    op, _, _, _ = oracle.sample_uniform(v, col, nrm, f, 30000, seed=11)
+    rng = np.random.default_rng(5)
+    # correspondences: nearest target strictly within the radius, -1 otherwise
+    q = op[:5000] + rng.normal(scale=0.01, size=(5000, 3))
+    idx = np.empty(len(q), np.int32); d2 = np.empty(len(q))
+    _lib.check(_lib.lib.otslam_cloud_nn_within(_lib.ptr(np.ascontiguousarray(q)), len(q), _lib.ptr(op), len(op), 0.012, _lib.ptr(idx),
+                                               _lib.ptr(d2), 0))
+    dist, nn = cKDTree(op).query(q)
+    inside = dist < 0.012
+    assert (idx >= 0).sum() == inside.sum() and ((idx >= 0) == inside).all()
+    diff = np.linalg.norm(q[inside] - op[idx[inside]], axis=1)
+    assert np.abs(diff - dist[inside]).max() <= 1e-12 and np.abs(np.sqrt(d2[inside]) - dist[inside]).max() <= 1e-12
+    # ICP: target = the cloud, source = the cloud moved by a small rotation + translation
+    a = 0.03
+    R = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]])
+    T_true = np.eye(4); T_true[:3, :3] = R; T_true[:3, 3] = [0.01, -0.008, 0.005]
+    src = o3d.geometry.PointCloud(op[::2].copy())
+    src.transform(np.linalg.inv(T_true))
+    tgt = o3d.geometry.PointCloud(op)
+    reg = o3d.pipelines.registration.registration_icp(
+        src, tgt, 0.05, np.eye(4), o3d.pipelines.registration.TransformationEstimationPointToPoint(),
+        o3d.pipelines.registration.ICPConvergenceCriteria(max_iteration=2000))
+    assert reg.fitness > 0.99 and reg.inlier_rmse < 2e-3
+    assert np.abs(reg.transformation - T_true).max() < 2e-3
+    before = o3d.pipelines.registration.evaluate_registration(src, tgt, 0.05)
+    assert before.inlier_rmse > 3 * reg.inlier_rmse and len(reg.correspondence_set) >= len(before.correspondence_set)
+    src.transform(reg.transformation)                                           # eval_table_chair.py:103
+    assert src.compute_point_cloud_distance(tgt).mean() < 1e-3
