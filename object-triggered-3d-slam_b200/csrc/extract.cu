@@ -91,10 +91,12 @@ constexpr int kFlagWords = 3 * (kVox / 32);   // 384 words: [axis][voxel bit], v
 
 __global__ void __launch_bounds__(256) mc_classify_kernel(ExtractCtx c, uint32_t* flags, uint8_t* cube_idx, int* tri_count) {
     __shared__ float tile[17 * 17 * 17];
+    __shared__ uint32_t s_flags[kFlagWords];      // edge bits of THIS block, merged into the global words once at the end
     __shared__ int nslot[8];
     __shared__ int s_tris;
     const int i = blockIdx.x;
     const int t = threadIdx.x;
+    for (int w = t; w < kFlagWords; w += 256) s_flags[w] = 0;
     const uint64_t key = c.bkeys[i];
     const int slot = c.bslots[i];
     int kx, ky, kz;
@@ -161,9 +163,13 @@ __global__ void __launch_bounds__(256) mc_classify_kernel(ExtractCtx c, uint32_t
                 const int ox = x + d_edge_shift[e][0], oy = y + d_edge_shift[e][1], oz = z + d_edge_shift[e][2];
                 const int axis = d_edge_shift[e][3];
                 const int nb = (ox >> 4) | ((oy >> 4) << 1) | ((oz >> 4) << 2);
-                const int os = nslot[nb];     // exists: the cube is valid, so that corner was observed
                 const int bit = (ox & 15) * 256 + (oy & 15) * 16 + (oz & 15);
-                atomicOr(flags + (size_t)os * kFlagWords + axis * (kVox / 32) + (bit >> 5), 1u << (bit & 31));
+                const int word = axis * (kVox / 32) + (bit >> 5);
+                if (nb == 0) {                // most edges belong to this block: shared-memory atomics (4 cubes share an edge)
+                    if (!(s_flags[word] & (1u << (bit & 31)))) atomicOr(&s_flags[word], 1u << (bit & 31));
+                } else {                      // the +x / +y / +z neighbour exists: the cube is valid, so that corner was observed
+                    atomicOr(flags + (size_t)nslot[nb] * kFlagWords + word, 1u << (bit & 31));
+                }
             }
         }
     }
@@ -171,6 +177,8 @@ __global__ void __launch_bounds__(256) mc_classify_kernel(ExtractCtx c, uint32_t
     if ((t & 31) == 0 && my_tris) atomicAdd(&s_tris, my_tris);
     __syncthreads();
     if (t == 0) tri_count[i] = s_tris;
+    for (int w = t; w < kFlagWords; w += 256)      // (the -x / -y / -z neighbours' cubes set bits of this block too: still an atomic)
+        if (s_flags[w]) atomicOr(flags + (size_t)slot * kFlagWords + w, s_flags[w]);
 }
 
 // per block: vertex count and exclusive per-word prefix of its edge bits
@@ -217,27 +225,45 @@ __device__ __forceinline__ void rec_color01(const uint4& r, double* c) {
     c[2] = __ddiv_rn(__ddiv_rn((double)(r.w & 0xFFFFFFu), dw), 255.0);
 }
 
+// One thread per VERTEX (round 1: one thread per 3 flag words, so the thread that owned a dense word produced up to 32
+// vertices -- ~600 FP64-heavy instructions each -- while its neighbours idled: 122 us for 747 k vertices).  The block's flag
+// words and their exclusive prefixes are staged in shared memory; vertex j of the block finds its word by binary search over
+// the prefixes and its bit with __fns (n-th set bit).  Vertex ids are unchanged (rank of the bit), so are the faces.
 __global__ void __launch_bounds__(128) mc_vertices_kernel(ExtractCtx c, const uint32_t* __restrict__ flags,
                                                           const uint16_t* __restrict__ word_prefix,
                                                           const int64_t* __restrict__ vbase, double* __restrict__ verts,
                                                           double* __restrict__ colors, int32_t* __restrict__ ekeys) {
     __shared__ int nslot[8];
+    __shared__ uint32_t s_bits[kFlagWords];
+    __shared__ uint16_t s_pre[kFlagWords];
     const int i = blockIdx.x, t = threadIdx.x;
     const uint64_t key = c.bkeys[i];
     const int slot = c.bslots[i];
-    if (vbase[i + 1] == vbase[i]) return;
+    const int nvb = (int)(vbase[i + 1] - vbase[i]);
+    if (nvb == 0) return;
     load_neighbours(c, key, slot, nslot);
+    for (int w = t; w < kFlagWords; w += 128) {
+        s_bits[w] = flags[(size_t)slot * kFlagWords + w];
+        s_pre[w] = word_prefix[(size_t)slot * kFlagWords + w];
+    }
     __syncthreads();
     int kx, ky, kz;
     unpack_key(key, kx, ky, kz);
     const uint4* blk = block_ptr(c.chunks, slot);
-    for (int wi = t; wi < kFlagWords; wi += 128) {
-        uint32_t bits = flags[(size_t)slot * kFlagWords + wi];
-        if (!bits) continue;
+    for (int j = t; j < nvb; j += 128) {
+        int lo = 0, hi = kFlagWords - 1;                  // last word whose exclusive prefix is <= j and that has a bit for j
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if ((int)s_pre[mid] <= j) lo = mid; else hi = mid - 1;
+        }
+        const int wi = lo;                                // (empty words share their successor's prefix: the search lands on the last
+                                                          //  word with prefix <= j, which is the non-empty one that contains rank j)
+        const uint32_t bits = s_bits[wi];
+        const int bit = (int)__fns(bits, 0, j - (int)s_pre[wi] + 1);
         const int axis = wi / (kVox / 32);
-        int64_t vid = vbase[i] + word_prefix[(size_t)slot * kFlagWords + wi];
-        for (; bits; bits &= bits - 1, ++vid) {
-            const int vox = (wi % (kVox / 32)) * 32 + (__ffs(bits) - 1);
+        const int64_t vid = vbase[i] + j;
+        {
+            const int vox = (wi % (kVox / 32)) * 32 + bit;
             const int x = vox >> 8, y = (vox >> 4) & 15, z = vox & 15;
             int q[3] = {x, y, z};
             q[axis] += 1;
