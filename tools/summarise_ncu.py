@@ -111,6 +111,9 @@ def full(path, out, traffic):
         rd, wr = val("dram__bytes_read.sum"), val("dram__bytes_write.sum")
         json.dump({"kernel": k, "source": os.path.basename(path), "dram_bytes_read": rd, "dram_bytes_write": wr,
                    "dram_bytes_per_launch": rd + wr, "launch_us": val("gpu__time_duration.sum"),
+                   "issue_active_frac": float(R[hdr.index("smsp__issue_active.avg.pct_of_peak_sustained_active")].replace(",", "")) / 100.0,
+                   "grid_size": int(float(R[hdr.index("launch__grid_size")].replace(",", ""))),
+                   "registers_per_thread": int(float(R[hdr.index("launch__registers_per_thread")].replace(",", ""))),
                    "note": "one launch = one 32-frame batch of the default bench workload (configs[1]: 640x480 / 5 mm chair+table)"},
                   open(os.path.join(ROOT, "profiles", "integrate_kernel_traffic.json"), "w"), indent=1)
 
