@@ -57,7 +57,7 @@ def parse():
     ap.add_argument("--hd-frames", type=int, default=2000, help="frames of the 1280x720 / 2 mm sub-run reported under \"hd\" (0 = skip)")
     ap.add_argument("--hd-steps", type=int, default=2)
     ap.add_argument("--hd-voxel", type=float, default=0.002)
-    ap.add_argument("--ingest-chunk", type=int, default=256, help="multi-GPU host ingest: frames per all-gathered chunk")
+    ap.add_argument("--ingest-chunk", type=int, default=128, help="multi-GPU host ingest: frames per all-gathered chunk")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-post", action="store_true")

@@ -265,38 +265,54 @@ def integrate_host_sharded(vol, depth, rgb, intr, extrinsics, rank, world, devic
         return
     plan = shard_plan(n, world, chunk_frames)
     per = plan[0][2]
-    side = torch.cuda.Stream(device=device)
+    copy_s = torch.cuda.Stream(device=device)       # H2D of this rank's share of chunk k+1 ...
+    side = torch.cuda.Stream(device=device)         # ... runs under the all-gather of chunk k (separate streams: the copy
+    #                                                 must not queue behind the previous chunk's collective)
     main = stream if stream is not None else torch.cuda.current_stream(device)
     bufs = [(torch.empty((per * world, H, W), dtype=depth.dtype, device=device),
              torch.empty((per * world, H, W, 3), dtype=rgb.dtype, device=device),
-             torch.cuda.Event(), torch.cuda.Event()) for _ in range(2)]
+             torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()) for _ in range(2)]
     local_off = [0]
+    import os as _os, time as _time
+    dbg = [] if _os.environ.get("OTSLAM_INGEST_DEBUG") else None
+    t_origin = _time.perf_counter()
 
     def issue(k):
         c0, nk, _ = plan[k]
-        gd, gc, ready, free = bufs[k & 1]
-        with torch.cuda.stream(side):
-            side.wait_event(free)                                   # the integration that last read this buffer
-            lo, hi = min(c0 + rank * per, c0 + nk), min(c0 + (rank + 1) * per, c0 + nk)
-            md, mc = gd[rank * per:(rank + 1) * per], gc[rank * per:(rank + 1) * per]
+        gd, gc, ready, free, copied = bufs[k & 1]
+        lo, hi = min(c0 + rank * per, c0 + nk), min(c0 + (rank + 1) * per, c0 + nk)
+        md, mc = gd[rank * per:(rank + 1) * per], gc[rank * per:(rank + 1) * per]
+        with torch.cuda.stream(copy_s):
+            copy_s.wait_event(free)                                 # the integration that last read this buffer
             if hi > lo:
                 src = local_off[0] if shards else lo
                 md[:hi - lo].copy_(depth[src:src + hi - lo], non_blocking=True)
                 mc[:hi - lo].copy_(rgb[src:src + hi - lo], non_blocking=True)
                 local_off[0] += hi - lo
+            copied.record(copy_s)
+        with torch.cuda.stream(side):
+            side.wait_event(copied)
             # in-place all-gather: every rank's share lands at its slot of the chunk buffer
             dist.all_gather_into_tensor(gd.view(torch.uint8), md.view(torch.uint8))      # NCCL in torch has no 16-bit integer type
             dist.all_gather_into_tensor(gc, mc)
             ready.record(side)
 
-    for _, _, _, free in bufs:
-        free.record(main)
+    for b in bufs:
+        b[3].record(main)
     issue(0)
     for k, (c0, nk, _) in enumerate(plan):
-        gd, gc, ready, free = bufs[k & 1]
+        gd, gc, ready, free, _ = bufs[k & 1]
         if k + 1 < len(plan):
             issue(k + 1)
         main.wait_event(ready)
+        if dbg is not None:
+            t_a = _time.perf_counter()
+            ready.synchronize()
+            t_b = _time.perf_counter()
         with torch.cuda.stream(main):       # integrate_batch orders the volume's own streams after torch's CURRENT stream
             vol.integrate_batch(gd[:nk], gc[:nk], intr, extrinsics[c0:c0 + nk], depth_scale, depth_trunc)   # returns when done
         free.record(main)
+        if dbg is not None:
+            dbg.append((k, 1e3 * (t_a - t_origin), 1e3 * (t_b - t_a), 1e3 * (_time.perf_counter() - t_b)))
+    if dbg is not None and rank == 0:
+        print("ingest chunks (k, issued at ms, waited for gather ms, integrate ms):", [tuple(round(x, 2) for x in d) for d in dbg], flush=True)
