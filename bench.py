@@ -11,10 +11,13 @@ filter kernels' own HBM figures; it is not part of `value` (the metric is frames
   value  : frames/s with the sequence already resident in HBM (kernel path only)
   e2e    : same metric through the public C-ABI call with HOST (pinned) buffers, H2D copies and a
            D2H read of the result statistics inside the timed region
+  e2e_full: the whole job, host frames -> final cloud in host memory (frame loop, extraction, sampling / gather, download)
   roofline: integrate_kernel, algorithmic bytes (40 B x N_upd + 5 B x W x H per frame)
-           / CUDA-event duration of that kernel, against MEASURED_PEAKS.json
-  cpu_baseline: the oracle (CPU port of the Open3D algorithm the reference calls) on a bounded
-           sample of the same sequence, all host threads
+           / CUDA-event duration of that kernel, against MEASURED_PEAKS.json; bound "issue" 
+  cpu_baseline: the oracle (CPU port of the Open3D algorithm the reference calls; real open3d when it imports) on a
+           bounded sample of the same sequence, all host threads; full_loop = incl. JPEG / PNG decode, loadtxt, inv
+  hd     : the same measurement on BASELINE configs[3]'s geometry (1280x720 x --hd-frames frames, 2 mm voxels), so that the
+           1/2/4/8-GPU runs record north_star's scaling config in the same JSON line
 
 Multi-GPU (torchrun, one rank per GPU): every rank receives every frame and integrates only its
 own spatial slab -- total work fixed => "scaling": "strong"; no per-frame collective.
