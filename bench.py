@@ -617,11 +617,13 @@ def measure(a, seq, world, rank, local, steps, warmup, with_e2e=True, hd=False):
             if world == 1:
                 nv, nf = vol.extract_mesh_resident()
                 t.append(time.perf_counter())
-                pts, cols, _ = vol.mesh_sample(100000, 0) if nv else (np.zeros((0, 3)), np.zeros((0, 3)), None)
-                keep = pts[:, 2] >= 0.03
-                res = (pts[keep], cols[keep])
+                if nv:      # as the drop-in script does it: sample and z mask stay in HBM, one (pinned) download of the survivors
+                    from otslam_b200.cloud import DeviceCloud
+                    res = DeviceCloud.sample_mesh(vol, 100000, 0, colors=True).zfilter(0.03).to_numpy()[:2]
+                else:
+                    res = (np.zeros((0, 3)), np.zeros((0, 3)))
                 t.append(time.perf_counter())
-                names = ("ingest+integrate", "extract_mesh+normals", "sample+download+z_mask")
+                names = ("ingest+integrate", "extract_mesh+normals", "sample+z_mask+download")
             else:
                 if not a.slab_halo:
                     slabmod.exchange_halo(vol, rank, world, device=dev)
