@@ -242,6 +242,37 @@ int otslam_cloud_rotate(const double* points, const double* normals, int64_t n, 
 int otslam_grid_smart_paste(uint8_t* base, const uint8_t* overlay, int width, int height, int x, int y, int w, int h,
                             int unknown_pixel, int threshold, int device);
 
+/* ---- the readers in front of the frame loop.  o3d.io.read_image(color_path) and
+ * o3d.io.read_image(depth_path) (3d_model/reconstruct_rgbd.py:90-91, reconstruct_rgbd_filter.py:88-89) decode the files
+ * ScannerNode::save_files wrote with cv::imwrite (ros2_ws/src/system_manager/src/scanner_node.cpp:268-283: baseline JPEG
+ * colour, 16-bit grey PNG depth; the gt_ / plain capture tools write 8-bit RGB PNG colour).  A decoder object takes a chunk of
+ * such files -- as paths or as bytes already in memory --, uploads the COMPRESSED bytes and runs inflate / PNG filters /
+ * Huffman / IDCT / upsampling / colour conversion on the GPU, into frame slots 0..n-1 kept in device memory, ready for
+ * otslam_decoder_integrate.  Results equal the stock decoders' (libpng; libjpeg's default islow IDCT + fancy upsampling) bit
+ * for bit.  Per-file status: 0 = decoded; 1 = a valid file of a kind the GPU decoders do not cover (progressive / grey /
+ * CMYK JPEG, interlaced or palette PNG, another image size ...): decode it with the stock decoder and otslam_decoder_put it;
+ * 2 = missing or damaged (CRC / structure), the reference's "Read image failed". */
+typedef struct otslam_decoder otslam_decoder;
+int otslam_decoder_create(int device, int height, int width, int max_frames, otslam_decoder** out);
+int otslam_decoder_destroy(otslam_decoder* d);
+/* n <= max_frames files per kind, read by host threads; either path array may be NULL (kind not wanted) */
+int otslam_decoder_decode_files(otslam_decoder* d, int n, const char* const* color_paths, const char* const* depth_paths,
+                                int32_t* color_status, int32_t* depth_status);
+/* the same for bytes in host memory: file i of a kind = blob[offsets[i] .. offsets[i + 1]) (empty = missing) */
+int otslam_decoder_decode(otslam_decoder* d, int n, const uint8_t* color_blob, const int64_t* color_offsets,
+                          const uint8_t* depth_blob, const int64_t* depth_offsets, int32_t* color_status, int32_t* depth_status);
+/* overwrite a slot with arrays decoded elsewhere (u16 [H][W], RGB8 [H][W][3]; host or device; either nullable) */
+int otslam_decoder_put(otslam_decoder* d, int slot, const uint16_t* depth, const uint8_t* rgb);
+/* copy slots [first, first + count) out (host or device pointers; either nullable) */
+int otslam_decoder_fetch(otslam_decoder* d, int first, int count, uint16_t* depth, uint8_t* rgb);
+/* volume.integrate(rgbd, intrinsic, extrinsic) (reconstruct_rgbd.py:106-109) for the slots listed (ascending), in that order;
+ * object_ids nullable (multi-object arenas).  The slots' contents are consumed (holes are closed in place). */
+int otslam_decoder_integrate(otslam_decoder* d, otslam_volume* v, int n_keep, const int32_t* slots, const double intr[4],
+                             const double* extrinsics, double depth_scale, double depth_trunc, const int32_t* object_ids);
+/* device times (CUDA events, ms) of the last decode: [0] inflate, [1] PNG filters + emit, [2] JPEG Huffman, [3] IDCT,
+ * [4] upsampling + colour; [5] = compressed bytes uploaded */
+int otslam_decoder_profile(otslam_decoder* d, double out[6]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -81,6 +81,14 @@ _SIGS = {
     "otslam_cloud_rotate": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _i]),
     "otslam_grid_smart_paste": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i]),
     "otslam_cloud_merge_pack": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _i]),
+    "otslam_decoder_create": (_i, [_i, _i, _i, _i, C.POINTER(_vp)]),
+    "otslam_decoder_destroy": (_i, [_vp]),
+    "otslam_decoder_decode_files": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
+    "otslam_decoder_decode": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "otslam_decoder_put": (_i, [_vp, _i, _vp, _vp]),
+    "otslam_decoder_fetch": (_i, [_vp, _i, _i, _vp, _vp]),
+    "otslam_decoder_integrate": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _d, _d, _vp]),
+    "otslam_decoder_profile": (_i, [_vp, _vp]),
 }
 EXPORTS = tuple(_SIGS)
 MISSING = []                        # tests assert this is empty: the .so must export the whole header

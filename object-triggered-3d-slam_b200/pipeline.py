@@ -181,6 +181,75 @@ class _Staging:
             _Staging._free.setdefault(self.key, []).append(self)
 
 
+last_decode_profile = []      # per chunk of the last GPU-decoded integrate_files call: decoder.FrameDecoder.profile() + counts
+
+
+def gpu_decode_enabled():
+    """OTSLAM_GPU_DECODE=0 keeps JPEG / PNG decoding on the host (OpenCV threads); default: the GPU decoders."""
+    return os.environ.get("OTSLAM_GPU_DECODE", "1") not in ("", "0")
+
+
+def _integrate_files_gpu(volume, triples, intrinsics, T_fix, depth_scale, depth_trunc, skip_errors, progress, on_error):
+    """integrate_files with the decoders on the GPU (decoder.py): a chunk's files are read by the library's host threads,
+    the compressed bytes are uploaded and decoded in HBM, and the decoded slots go straight into the volume.  Chunk k+1 is
+    read + decoded (a worker thread, the decoder's own streams) while chunk k integrates.  Frames the GPU decoders pass on
+    (status != 0: progressive JPEG, another size, a damaged or missing file ...) go through the stock decoders exactly as in
+    the host path, so warnings, exceptions and skip semantics are the host path's."""
+    from concurrent.futures import ThreadPoolExecutor
+    from .decoder import FrameDecoder
+    H, W = intrinsics.height, intrinsics.width
+    n = len(triples)
+    chunks = [triples[c0:c0 + CHUNK_FRAMES] for c0 in range(0, n, CHUNK_FRAMES)]
+    vol = volume._vol
+    del last_decode_profile[:]
+    decs = [FrameDecoder(H, W, min(CHUNK_FRAMES, n), vol.device) for _ in range(2 if len(chunks) > 1 else 1)]
+    done = 0
+    try:
+        with ThreadPoolExecutor(max_workers=_decode_workers()) as pool, ThreadPoolExecutor(max_workers=1) as stage:
+            def prepare(ci):
+                dec, chunk = decs[ci % len(decs)], chunks[ci]
+                cstat, dstat = dec.decode_files([t[0] for t in chunk], [t[1] for t in chunk])
+                prof = dec.profile()
+                prof["frames"], prof["passed_on"] = len(chunk), int(np.count_nonzero(cstat | dstat))
+                last_decode_profile.append(prof)
+
+                def finish(k):
+                    try:
+                        if cstat[k] or dstat[k]:
+                            d, c = np.empty((H, W), np.uint16), np.empty((H, W, 3), np.uint8)
+                            ext, err = _decode_into(chunk[k], intrinsics, T_fix, d, c)
+                            if err is None:
+                                dec.put(k, d, c)
+                            return ext, err
+                        return np.linalg.inv(read_pose(chunk[k][2]) @ T_fix), None
+                    except Exception as err:  # noqa: BLE001
+                        return None, err
+                return list(pool.map(finish, range(len(chunk))))
+
+            pending = stage.submit(prepare, 0)
+            for ci, chunk in enumerate(chunks):
+                res = pending.result()
+                pending = stage.submit(prepare, ci + 1) if ci + 1 < len(chunks) else None
+                slots, exts = [], []
+                for k, ((ext, err), triple) in enumerate(zip(res, chunk)):
+                    if err is not None:
+                        if not skip_errors:
+                            raise err
+                        if on_error:
+                            on_error(triple[3], err)
+                        continue
+                    slots.append(k); exts.append(ext)
+                    if progress:
+                        progress(triple[3], ci * CHUNK_FRAMES + k + 1, n)
+                if exts:
+                    decs[ci % len(decs)].integrate(vol, slots, intrinsics.fxfycxcy(), np.stack(exts), depth_scale, depth_trunc)
+                    done += len(slots)
+    finally:
+        for dec in decs:
+            dec.close()
+    return done
+
+
 def integrate_files(volume, triples, intrinsics, T_fix, depth_scale=1000.0, depth_trunc=3.0, skip_errors=False,
                     progress=None, on_error=None):
     """Integrate capture triples [(color, depth, pose, label)] in order. Returns frames integrated.
@@ -192,11 +261,14 @@ def integrate_files(volume, triples, intrinsics, T_fix, depth_scale=1000.0, dept
     on the first bad frame, or print-and-skip -- and the frame order seen by the volume are exactly the
     sequential loop's."""
     from concurrent.futures import ThreadPoolExecutor
+    from .volume import TSDFVolume
     done = 0
     n = len(triples)
     chunks = [triples[c0:c0 + CHUNK_FRAMES] for c0 in range(0, n, CHUNK_FRAMES)]
     if not chunks:
         return 0
+    if gpu_decode_enabled() and not sidecar_enabled() and isinstance(getattr(volume, "_vol", None), TSDFVolume):
+        return _integrate_files_gpu(volume, triples, intrinsics, T_fix, depth_scale, depth_trunc, skip_errors, progress, on_error)
     staging = _Staging.acquire(min(CHUNK_FRAMES, n), intrinsics.height, intrinsics.width, 2 if len(chunks) > 1 else 1)
     try:
         with ThreadPoolExecutor(max_workers=_decode_workers()) as pool:
