@@ -374,9 +374,9 @@ def files_e2e(a, seq, n_files=768):
     scanner_node.cpp writes them) -> pipeline.integrate_files (thread-pool decode one chunk ahead of the GPU) into
     a fresh ScalableTSDFVolume.  File decoding, not the GPU, bounds this number; the sequential decode rate is what
     the reference's own per-frame loop (reconstruct_rgbd.py:86-109) pays on top of its CPU integration."""
-    import glob
     import shutil
     import tempfile
+    import numpy as np
     import otslam_b200.o3d_compat as o3d
     from otslam_b200 import pipeline, synth
     depth, rgb = seq.numpy()
@@ -427,6 +427,25 @@ def files_e2e(a, seq, n_files=768):
                "sequential_decode_frames_per_s": seq_decode_fps,
                "note": "capture tree on disk -> frames in the volume; default = GPU decoders (host threads only read and frame the "
                        "files), host_decode = OpenCV threads (OTSLAM_GPU_DECODE=0), sequential = the reference's one-core loop"}
+        # (3) the decoders alone: one chunk of files -> decoded frames in HBM (file reads from the page cache, upload of the
+        # compressed bytes and all six kernels inside the timed call)
+        try:
+            from otslam_b200.decoder import FrameDecoder
+            m = min(pipeline.CHUNK_FRAMES, len(triples))
+            dec = FrameDecoder(int(seq.intr[1]), int(seq.intr[0]), m)
+            cps, dps = [t[0] for t in triples[:m]], [t[1] for t in triples[:m]]
+            dec.decode_files(cps, dps)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                cs, ds = dec.decode_files(cps, dps)
+            dt3 = (time.perf_counter() - t0) / 3
+            prof = dec.profile()
+            out["decode_only"] = {"frames": m, "frames_per_s": m / dt3, "wall_ms": 1e3 * dt3, "all_decoded": bool((cs == 0).all() and (ds == 0).all()),
+                                  "device_ms": {k: prof[k] for k in keys},
+                                  "decoded_GBps": m * seq.intr[0] * seq.intr[1] * 5 / dt3 / 1e9}
+            dec.close()
+        except Exception as e:  # noqa: BLE001
+            out["decode_only"] = {"error": repr(e)}
         # the same loop served from the raw side-car (OTSLAM_SIDECAR=1: decoded frames cached next to the tree on the first
         # pass): identical volumes, no JPEG / PNG decode on later passes
         os.environ["OTSLAM_SIDECAR"] = "1"

@@ -52,6 +52,7 @@ struct InflateTables {            // 3.6 KB: one per decoder (shared memory on t
     uint16_t dist_count[16], dist_symbol[32];
     uint16_t len_count[16], len_symbol[19];
     uint16_t lengths[320];
+    int32_t build_status;             // lane 0's verdict on a table set, read by the whole team after the barrier
 };
 
 struct BitsLSB {                  // deflate packs bits starting at the least significant bit of each byte
@@ -153,14 +154,30 @@ IC_FN inline int huff_decode(BitsLSB& b, const uint16_t* fast, int fast_bits, co
     return -1;
 }
 
-IC_FN inline int inflate_codes(BitsLSB& b, uint8_t* out, int64_t& pos, int64_t cap, const InflateTables& T, bool& full) {
+// ---- a TEAM of `nlanes` threads runs the decoder in lock step (on the GPU: the 32 lanes of a warp; on the host: 1).  Every
+// lane decodes the same symbols from the same bytes (uniform control flow, table reads are broadcasts), so no lane ever
+// waits for another to learn what comes next; the work that is parallel -- copying a match of up to 258 bytes, a stored
+// block -- is split across the lanes (lane l moves bytes l, l + nlanes, ...).  Tables are built by lane 0 between two team
+// barriers.  IC_TEAM_SYNC() = the barrier (orders the team's memory accesses): __syncwarp() in kernels, nothing for a
+// team of one; the CPU model defines it as a thread barrier to run teams of several threads.
+#ifndef IC_TEAM_SYNC
+#if defined(__CUDA_ARCH__)
+#define IC_TEAM_SYNC() __syncwarp()
+#else
+#define IC_TEAM_SYNC() ((void)0)
+#endif
+#endif
+
+IC_FN inline int inflate_codes(BitsLSB& b, uint8_t* out, int64_t& pos, int64_t cap, const InflateTables& T, bool& full, int lane,
+                               int nlanes) {
     for (;;) {
         b.refill();
         int sym = huff_decode(b, T.lit_fast, kLitFast, T.lit_count, T.lit_symbol);
         if (sym < 0 || b.cnt < 0) return IC_CORRUPT;
         if (sym < 256) {
             if (pos >= cap) { full = true; return IC_OK; }
-            out[pos++] = (uint8_t)sym;
+            if (lane == 0) out[pos] = (uint8_t)sym;
+            ++pos;
             continue;
         }
         if (sym == 256) return IC_OK;
@@ -186,15 +203,23 @@ IC_FN inline int inflate_codes(BitsLSB& b, uint8_t* out, int64_t& pos, int64_t c
         if (len > cap - pos) { len = (int)(cap - pos); full = true; }
         const uint8_t* src = out + pos - dist;
         uint8_t* dst = out + pos;
-        for (int i = 0; i < len; ++i) dst[i] = src[i];       // byte order matters: the ranges may overlap
+        IC_TEAM_SYNC();                                      // everything before `pos` is written, by whichever lane
+        if (dist >= len) {
+            for (int i = lane; i < len; i += nlanes) dst[i] = src[i];
+        } else {                                             // the match overlaps itself: the last `dist` bytes repeat
+            const int d = (int)dist;
+            for (int i = lane; i < len; i += nlanes) dst[i] = src[i % d];
+        }
         pos += len;
         if (full) return IC_OK;
     }
 }
 
 // zlib stream -> out[0..cap).  Stops when `cap` bytes exist (a PNG decoder ignores what follows the last scan line).
-// *out_len = bytes produced.  The Adler-32 trailer is not verified (documented in DESIGN.md).
-IC_FN inline int inflate_zlib(const uint8_t* in, int64_t in_len, uint8_t* out, int64_t cap, InflateTables& T, int64_t* out_len) {
+// *out_len = bytes produced.  The Adler-32 trailer is not verified (documented in DESIGN.md).  Every lane of the team calls
+// this with the same arguments and gets the same result; out[] is complete after a final IC_TEAM_SYNC() by the caller.
+IC_FN inline int inflate_zlib(const uint8_t* in, int64_t in_len, uint8_t* out, int64_t cap, InflateTables& T, int64_t* out_len,
+                              int lane = 0, int nlanes = 1) {
     *out_len = 0;
     if (in_len < 2) return IC_CORRUPT;
     const int cmf = in[0], flg = in[1];
@@ -219,19 +244,23 @@ IC_FN inline int inflate_zlib(const uint8_t* in, int64_t in_len, uint8_t* out, i
             if (len != (~nlen & 0xFFFFu) || (int64_t)len > b.end - b.p) return IC_CORRUPT;
             int64_t n = len;
             if (n > cap - pos) { n = cap - pos; full = true; }
-            for (int64_t i = 0; i < n; ++i) out[pos + i] = b.p[i];
+            for (int64_t i = lane; i < n; i += nlanes) out[pos + i] = b.p[i];
             pos += n;
             b.p += len;
         } else if (type == 1) {
-            int s = 0;
-            for (; s < 144; ++s) T.lengths[s] = 8;
-            for (; s < 256; ++s) T.lengths[s] = 9;
-            for (; s < 280; ++s) T.lengths[s] = 7;
-            for (; s < 288; ++s) T.lengths[s] = 8;
-            huff_construct(T.lit_count, T.lit_symbol, T.lengths, 288, T.lit_fast, kLitFast);
-            for (s = 0; s < 30; ++s) T.lengths[s] = 5;
-            huff_construct(T.dist_count, T.dist_symbol, T.lengths, 30, T.dist_fast, kDistFast);
-            const int r = inflate_codes(b, out, pos, cap, T, full);
+            IC_TEAM_SYNC();                                   // nobody still decodes with the previous block's tables
+            if (lane == 0) {
+                int s = 0;
+                for (; s < 144; ++s) T.lengths[s] = 8;
+                for (; s < 256; ++s) T.lengths[s] = 9;
+                for (; s < 280; ++s) T.lengths[s] = 7;
+                for (; s < 288; ++s) T.lengths[s] = 8;
+                huff_construct(T.lit_count, T.lit_symbol, T.lengths, 288, T.lit_fast, kLitFast);
+                for (s = 0; s < 30; ++s) T.lengths[s] = 5;
+                huff_construct(T.dist_count, T.dist_symbol, T.lengths, 30, T.dist_fast, kDistFast);
+            }
+            IC_TEAM_SYNC();
+            const int r = inflate_codes(b, out, pos, cap, T, full, lane, nlanes);
             if (r != IC_OK) return r;
         } else if (type == 2) {
             b.refill();
@@ -241,39 +270,64 @@ IC_FN inline int inflate_zlib(const uint8_t* in, int64_t in_len, uint8_t* out, i
             const uint64_t lo = 16ull | (17ull << 5) | (18ull << 10) | (0ull << 15) | (8ull << 20) | (7ull << 25) | (9ull << 30) |
                                 (6ull << 35) | (10ull << 40) | (5ull << 45) | (11ull << 50) | (4ull << 55);
             const uint64_t hi = 12ull | (3ull << 5) | (13ull << 10) | (2ull << 15) | (14ull << 20) | (1ull << 25) | (15ull << 30);
-            for (int i = 0; i < 19; ++i) T.lengths[i] = 0;
+            // the 19 lengths are small: every lane keeps its own copy in registers / local memory until lane 0 publishes them
+            uint16_t cl[19];
+            for (int i = 0; i < 19; ++i) cl[i] = 0;
             for (int i = 0; i < ncode; ++i) {
                 b.refill();
                 const int ord = (int)((i < 12 ? lo >> (5 * i) : hi >> (5 * (i - 12))) & 31u);
-                T.lengths[ord] = (uint16_t)b.bits(3);
+                cl[ord] = (uint16_t)b.bits(3);
             }
             if (b.cnt < 0) return IC_CORRUPT;
-            if (huff_construct(T.len_count, T.len_symbol, T.lengths, 19, nullptr, 0) != 0) return IC_CORRUPT;
-            int idx = 0;
+            IC_TEAM_SYNC();                                   // the previous block's tables (and T.lengths) are no longer read
+            if (lane == 0) {
+                for (int i = 0; i < 19; ++i) T.lengths[i] = cl[i];
+                T.build_status = huff_construct(T.len_count, T.len_symbol, T.lengths, 19, nullptr, 0);
+            }
+            IC_TEAM_SYNC();
+            if (T.build_status != 0) return IC_CORRUPT;
+            // the literal/length + distance code lengths: decoded by every lane (the decisions depend on them), stored by lane 0
+            int idx = 0, prev = 0;
             while (idx < nlen + ndist) {
                 b.refill();
                 const int sym = huff_decode(b, nullptr, 0, T.len_count, T.len_symbol);
                 if (sym < 0 || b.cnt < 0) return IC_CORRUPT;
                 if (sym < 16) {
-                    T.lengths[idx++] = (uint16_t)sym;
+                    if (lane == 0) T.lengths[idx] = (uint16_t)sym;
+                    ++idx;
+                    prev = sym;
                 } else {
                     int rep, val = 0;
                     if (sym == 16) {
                         if (idx == 0) return IC_CORRUPT;
-                        val = T.lengths[idx - 1];
+                        val = prev;
                         rep = 3 + (int)b.bits(2);
                     } else if (sym == 17) rep = 3 + (int)b.bits(3);
                     else rep = 11 + (int)b.bits(7);
                     if (b.cnt < 0 || idx + rep > nlen + ndist) return IC_CORRUPT;
-                    while (rep--) T.lengths[idx++] = (uint16_t)val;
+                    if (lane == 0)
+                        for (int k = 0; k < rep; ++k) T.lengths[idx + k] = (uint16_t)val;
+                    idx += rep;
+                    prev = val;
                 }
             }
-            if (T.lengths[256] == 0) return IC_CORRUPT;          // no end-of-block code
-            int e = huff_construct(T.lit_count, T.lit_symbol, T.lengths, nlen, T.lit_fast, kLitFast);
-            if (e < 0 || (e > 0 && nlen != T.lit_count[0] + T.lit_count[1])) return IC_CORRUPT;   // incomplete: only a lone 1-bit code
-            e = huff_construct(T.dist_count, T.dist_symbol, T.lengths + nlen, ndist, T.dist_fast, kDistFast);
-            if (e < 0 || (e > 0 && ndist != T.dist_count[0] + T.dist_count[1])) return IC_CORRUPT;
-            const int r = inflate_codes(b, out, pos, cap, T, full);
+            IC_TEAM_SYNC();                                   // (the code-length tables are done with; lane 0's stores are complete)
+            if (lane == 0) {
+                int st = IC_OK;
+                if (T.lengths[256] == 0) st = IC_CORRUPT;     // no end-of-block code
+                if (st == IC_OK) {
+                    const int e = huff_construct(T.lit_count, T.lit_symbol, T.lengths, nlen, T.lit_fast, kLitFast);
+                    if (e < 0 || (e > 0 && nlen != T.lit_count[0] + T.lit_count[1])) st = IC_CORRUPT;   // incomplete: only a lone 1-bit code
+                }
+                if (st == IC_OK) {
+                    const int e = huff_construct(T.dist_count, T.dist_symbol, T.lengths + nlen, ndist, T.dist_fast, kDistFast);
+                    if (e < 0 || (e > 0 && ndist != T.dist_count[0] + T.dist_count[1])) st = IC_CORRUPT;
+                }
+                T.build_status = st;
+            }
+            IC_TEAM_SYNC();
+            if (T.build_status != IC_OK) return IC_CORRUPT;
+            const int r = inflate_codes(b, out, pos, cap, T, full, lane, nlanes);
             if (r != IC_OK) return r;
         } else {
             return IC_CORRUPT;

@@ -189,47 +189,81 @@ def gpu_decode_enabled():
     return os.environ.get("OTSLAM_GPU_DECODE", "1") not in ("", "0")
 
 
+_decoder_pool = {}            # (height, width, frames, device) -> idle FrameDecoders (device + pinned buffers are kept)
+_decoder_lock = None
+
+
+def _acquire_decoders(count, height, width, frames, device):
+    import threading
+    from .decoder import FrameDecoder
+    global _decoder_lock
+    if _decoder_lock is None:
+        _decoder_lock = threading.Lock()
+    key = (height, width, frames, device)
+    with _decoder_lock:
+        idle = _decoder_pool.setdefault(key, [])
+        got = [idle.pop() for _ in range(min(count, len(idle)))]
+    return got + [FrameDecoder(height, width, frames, device) for _ in range(count - len(got))], key
+
+
+def release_decoders():
+    """Free the pooled GPU decoders (their device and page-locked staging buffers)."""
+    for idle in _decoder_pool.values():
+        while idle:
+            idle.pop().close()
+
+
+import atexit                                                     # noqa: E402
+atexit.register(release_decoders)                                 # before the CUDA runtime is torn down
+
+
 def _integrate_files_gpu(volume, triples, intrinsics, T_fix, depth_scale, depth_trunc, skip_errors, progress, on_error):
     """integrate_files with the decoders on the GPU (decoder.py): a chunk's files are read by the library's host threads,
-    the compressed bytes are uploaded and decoded in HBM, and the decoded slots go straight into the volume.  Chunk k+1 is
-    read + decoded (a worker thread, the decoder's own streams) while chunk k integrates.  Frames the GPU decoders pass on
+    the compressed bytes are uploaded and decoded in HBM, and the decoded slots go straight into the volume.  Two chunks are
+    in preparation (read + upload + decode: two worker threads, three decoders with their own streams) while a third
+    integrates; the pose files are parsed by the thread pool while the library call decodes.  Frames the GPU decoders pass on
     (status != 0: progressive JPEG, another size, a damaged or missing file ...) go through the stock decoders exactly as in
     the host path, so warnings, exceptions and skip semantics are the host path's."""
     from concurrent.futures import ThreadPoolExecutor
-    from .decoder import FrameDecoder
     H, W = intrinsics.height, intrinsics.width
     n = len(triples)
     chunks = [triples[c0:c0 + CHUNK_FRAMES] for c0 in range(0, n, CHUNK_FRAMES)]
     vol = volume._vol
     del last_decode_profile[:]
-    decs = [FrameDecoder(H, W, min(CHUNK_FRAMES, n), vol.device) for _ in range(2 if len(chunks) > 1 else 1)]
+    ahead = min(2, len(chunks))                                   # chunks in preparation beside the one integrating
+    decs, pool_key = _acquire_decoders(min(3, len(chunks)), H, W, CHUNK_FRAMES, vol.device)
     done = 0
     try:
-        with ThreadPoolExecutor(max_workers=_decode_workers()) as pool, ThreadPoolExecutor(max_workers=1) as stage:
+        with ThreadPoolExecutor(max_workers=_decode_workers()) as pool, ThreadPoolExecutor(max_workers=ahead) as stage:
+            def pose(k, chunk):
+                try:
+                    return np.linalg.inv(read_pose(chunk[k][2]) @ T_fix), None
+                except Exception as err:  # noqa: BLE001
+                    return None, err
+
+            def stock(k, chunk, dec):
+                """the reference's per-frame body on the host for a frame the GPU decoders passed on"""
+                d, c = np.empty((H, W), np.uint16), np.empty((H, W, 3), np.uint8)
+                ext, err = _decode_into(chunk[k], intrinsics, T_fix, d, c)
+                if err is None:
+                    dec.put(k, d, c)
+                return ext, err
+
             def prepare(ci):
                 dec, chunk = decs[ci % len(decs)], chunks[ci]
+                poses = [pool.submit(pose, k, chunk) for k in range(len(chunk))]         # parsed while the call below decodes
                 cstat, dstat = dec.decode_files([t[0] for t in chunk], [t[1] for t in chunk])
                 prof = dec.profile()
                 prof["frames"], prof["passed_on"] = len(chunk), int(np.count_nonzero(cstat | dstat))
                 last_decode_profile.append(prof)
+                redo = {k: pool.submit(stock, k, chunk, dec) for k in np.nonzero(cstat | dstat)[0]}
+                return [(redo[k] if k in redo else poses[k]).result() for k in range(len(chunk))]
 
-                def finish(k):
-                    try:
-                        if cstat[k] or dstat[k]:
-                            d, c = np.empty((H, W), np.uint16), np.empty((H, W, 3), np.uint8)
-                            ext, err = _decode_into(chunk[k], intrinsics, T_fix, d, c)
-                            if err is None:
-                                dec.put(k, d, c)
-                            return ext, err
-                        return np.linalg.inv(read_pose(chunk[k][2]) @ T_fix), None
-                    except Exception as err:  # noqa: BLE001
-                        return None, err
-                return list(pool.map(finish, range(len(chunk))))
-
-            pending = stage.submit(prepare, 0)
+            futs = {ci: stage.submit(prepare, ci) for ci in range(ahead)}
             for ci, chunk in enumerate(chunks):
-                res = pending.result()
-                pending = stage.submit(prepare, ci + 1) if ci + 1 < len(chunks) else None
+                res = futs.pop(ci).result()
+                if ci + ahead < len(chunks):                       # its decoder's previous chunk (ci - 1) has been integrated
+                    futs[ci + ahead] = stage.submit(prepare, ci + ahead)
                 slots, exts = [], []
                 for k, ((ext, err), triple) in enumerate(zip(res, chunk)):
                     if err is not None:
@@ -245,8 +279,8 @@ def _integrate_files_gpu(volume, triples, intrinsics, T_fix, depth_scale, depth_
                     decs[ci % len(decs)].integrate(vol, slots, intrinsics.fxfycxcy(), np.stack(exts), depth_scale, depth_trunc)
                     done += len(slots)
     finally:
-        for dec in decs:
-            dec.close()
+        with _decoder_lock:
+            _decoder_pool.setdefault(pool_key, []).extend(decs)
     return done
 
 

@@ -1,16 +1,55 @@
 // CPU model of csrc/imgcodec.cu: the same __host__ __device__ functions (csrc/imgcodec_core.h) composed the way the
 // kernels compose them, compiled with g++ by tests/test_imgcodec_model.py and compared with OpenCV's decoders.
 // Test infrastructure only -- the product library never runs these functions on the host.
+#include <pthread.h>
 #include <stdlib.h>
 
+#include <thread>
 #include <vector>
+
+// the decoder's team barrier (a warp's __syncwarp() on the GPU) as a thread barrier, so that teams of several host threads
+// exercise the same synchronisation points
+static thread_local pthread_barrier_t* g_team_barrier = nullptr;
+#define IC_TEAM_SYNC()                                              \
+    do {                                                            \
+        if (g_team_barrier) pthread_barrier_wait(g_team_barrier);   \
+    } while (0)
 
 #include "../../object-triggered-3d-slam_b200/csrc/imgcodec_core.h"
 
 using namespace imgcodec;
 
+// inflate with a team of `team` threads in lock step (team == 1: plain call)
+static int team_inflate(const uint8_t* z, int64_t z_len, uint8_t* raw, int64_t cap, int team, int64_t* got) {
+    InflateTables* T = new InflateTables;
+    int st = IC_OK;
+    if (team <= 1) {
+        st = inflate_zlib(z, z_len, raw, cap, *T, got);
+    } else {
+        pthread_barrier_t bar;
+        pthread_barrier_init(&bar, nullptr, (unsigned)team);
+        std::vector<int> sts((size_t)team, IC_OK);
+        std::vector<int64_t> gots((size_t)team, 0);
+        std::vector<std::thread> th;
+        for (int l = 0; l < team; ++l)
+            th.emplace_back([&, l] {
+                g_team_barrier = &bar;
+                sts[l] = inflate_zlib(z, z_len, raw, cap, *T, &gots[l], l, team);
+                g_team_barrier = nullptr;
+            });
+        for (auto& t : th) t.join();
+        pthread_barrier_destroy(&bar);
+        st = sts[0];
+        *got = gots[0];
+        for (int l = 1; l < team; ++l)
+            if (sts[l] != st || gots[l] != *got) st = 77;          // the lanes must agree
+    }
+    delete T;
+    return st;
+}
+
 extern "C" int model_decode_png(const uint8_t* file, int64_t size, int H, int W, int band_rows, int check_crc, uint8_t* out,
-                                int* channels) {
+                                int* channels, int team) {
     static const Crc32 crc;
     std::vector<uint8_t> z((size_t)size);
     PngFrame f;
@@ -18,20 +57,13 @@ extern "C" int model_decode_png(const uint8_t* file, int64_t size, int H, int W,
     *channels = f.channels;
     const int64_t cap = (int64_t)(f.rowbytes + 1) * f.height;
     std::vector<uint8_t> raw((size_t)cap);
-    InflateTables* T = new InflateTables;
     int64_t got = 0;
-    int st = inflate_zlib(z.data(), f.z_len, raw.data(), cap, *T, &got);
-    delete T;
+    int st = team_inflate(z.data(), f.z_len, raw.data(), cap, team, &got);
     if (st != IC_OK) return st;
     if (got != cap) return IC_CORRUPT;                           // "Not enough image data"
     if (band_rows < 1) band_rows = 1;
     const int n_bands = (f.height + band_rows - 1) / band_rows;
     // bands in reverse order on purpose: they must be independent of each other
-    for (int b = n_bands - 1; b >= 0; --b) {
-        const int r0 = png_band_first(raw.data(), f.height, f.rowbytes + 1, b * band_rows);
-        const int r1 = png_band_first(raw.data(), f.height, f.rowbytes + 1, (b + 1) * band_rows);
-        (void)r1;
-    }
     std::vector<int> first(n_bands + 1);
     for (int b = 0; b <= n_bands; ++b) first[b] = b == n_bands ? f.height : png_band_first(raw.data(), f.height, f.rowbytes + 1, b * band_rows);
     for (int b = n_bands - 1; b >= 0; --b)

@@ -156,7 +156,7 @@ def test_frame_loop_from_files_gpu_decode_equals_host_decode(frames, tmp_path, m
     vol = _volume(o3d)
     with pytest.raises(Exception):
         pipeline.integrate_files(vol, triples, intr, synth.T_FIX)
-    assert vol._vol.stats()[1] > 0                               # chunk 0 (frames 1-4) went in before frame 5 failed
+    assert vol._vol.stats()["weight_sum"] > 0                               # chunk 0 (frames 1-4) went in before frame 5 failed
 
 
 def test_hd_frames_gpu_decode(tmp_path):
