@@ -168,21 +168,25 @@ IC_FN inline int huff_decode(BitsLSB& b, const uint16_t* fast, int fast_bits, co
 #endif
 #endif
 
-IC_FN inline int inflate_codes(BitsLSB& b, uint8_t* out, int64_t& pos, int64_t cap, const InflateTables& T, bool& full, int lane,
+IC_FN inline int inflate_codes(BitsLSB& b, uint8_t* out, int64_t& pos64, int64_t cap64, const InflateTables& T, bool& full, int lane,
                                int nlanes) {
+    // 32-bit positions inside the loop (an image's scan lines are < 2^31 bytes: the decoder object caps height x width)
+    int pos = (int)pos64;
+    const int cap = (int)cap64;
+    int status = IC_OK;
     for (;;) {
         b.refill();
         int sym = huff_decode(b, T.lit_fast, kLitFast, T.lit_count, T.lit_symbol);
-        if (sym < 0 || b.cnt < 0) return IC_CORRUPT;
+        if (sym < 0 || b.cnt < 0) { status = IC_CORRUPT; break; }
         if (sym < 256) {
-            if (pos >= cap) { full = true; return IC_OK; }
+            if (pos >= cap) { full = true; break; }
             if (lane == 0) out[pos] = (uint8_t)sym;
             ++pos;
             continue;
         }
-        if (sym == 256) return IC_OK;
+        if (sym == 256) break;
         sym -= 257;
-        if (sym >= 29) return IC_CORRUPT;
+        if (sym >= 29) { status = IC_CORRUPT; break; }
         int len;
         if (sym < 8) len = 3 + sym;
         else if (sym == 28) len = 258;
@@ -192,27 +196,28 @@ IC_FN inline int inflate_codes(BitsLSB& b, uint8_t* out, int64_t& pos, int64_t c
         }
         b.refill();
         const int ds = huff_decode(b, T.dist_fast, kDistFast, T.dist_count, T.dist_symbol);
-        if (ds < 0 || ds >= 30) return IC_CORRUPT;
-        int64_t dist;
+        if (ds < 0 || ds >= 30) { status = IC_CORRUPT; break; }
+        int dist;
         if (ds < 4) dist = 1 + ds;
         else {
             const int eb = (ds >> 1) - 1;
-            dist = 1 + ((int64_t)(2 + (ds & 1)) << eb) + (int64_t)b.bits(eb);
+            dist = 1 + ((2 + (ds & 1)) << eb) + (int)b.bits(eb);
         }
-        if (b.cnt < 0 || dist > pos) return IC_CORRUPT;
-        if (len > cap - pos) { len = (int)(cap - pos); full = true; }
-        const uint8_t* src = out + pos - dist;
+        if (b.cnt < 0 || dist > pos) { status = IC_CORRUPT; break; }
+        if (len > cap - pos) { len = cap - pos; full = true; }
+        const uint8_t* src = out + (pos - dist);
         uint8_t* dst = out + pos;
         IC_TEAM_SYNC();                                      // everything before `pos` is written, by whichever lane
         if (dist >= len) {
             for (int i = lane; i < len; i += nlanes) dst[i] = src[i];
         } else {                                             // the match overlaps itself: the last `dist` bytes repeat
-            const int d = (int)dist;
-            for (int i = lane; i < len; i += nlanes) dst[i] = src[i % d];
+            for (int i = lane; i < len; i += nlanes) dst[i] = src[i % dist];
         }
         pos += len;
-        if (full) return IC_OK;
+        if (full) break;
     }
+    pos64 = pos;
+    return status;
 }
 
 // zlib stream -> out[0..cap).  Stops when `cap` bytes exist (a PNG decoder ignores what follows the last scan line).

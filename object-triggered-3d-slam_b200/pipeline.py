@@ -15,6 +15,7 @@ import numpy as np
 from .o3d_compat import io as o3d_io
 
 CHUNK_FRAMES = 256
+DECODE_AHEAD = 3              # GPU decode: chunks being read / uploaded / decoded while one integrates
 _FMT = "[ScalableTSDFVolume::Integrate] Unsupported image format."
 
 
@@ -219,9 +220,9 @@ atexit.register(release_decoders)                                 # before the C
 
 def _integrate_files_gpu(volume, triples, intrinsics, T_fix, depth_scale, depth_trunc, skip_errors, progress, on_error):
     """integrate_files with the decoders on the GPU (decoder.py): a chunk's files are read by the library's host threads,
-    the compressed bytes are uploaded and decoded in HBM, and the decoded slots go straight into the volume.  Two chunks are
-    in preparation (read + upload + decode: two worker threads, three decoders with their own streams) while a third
-    integrates; the pose files are parsed by the thread pool while the library call decodes.  Frames the GPU decoders pass on
+    the compressed bytes are uploaded and decoded in HBM, and the decoded slots go straight into the volume.  DECODE_AHEAD
+    chunks are in preparation (read + upload + decode: one worker thread and one decoder with its own streams each) while
+    another integrates; the pose files are parsed by the thread pool while the library call decodes.  Frames the GPU decoders pass on
     (status != 0: progressive JPEG, another size, a damaged or missing file ...) go through the stock decoders exactly as in
     the host path, so warnings, exceptions and skip semantics are the host path's."""
     from concurrent.futures import ThreadPoolExecutor
@@ -230,8 +231,11 @@ def _integrate_files_gpu(volume, triples, intrinsics, T_fix, depth_scale, depth_
     chunks = [triples[c0:c0 + CHUNK_FRAMES] for c0 in range(0, n, CHUNK_FRAMES)]
     vol = volume._vol
     del last_decode_profile[:]
-    ahead = min(2, len(chunks))                                   # chunks in preparation beside the one integrating
-    decs, pool_key = _acquire_decoders(min(3, len(chunks)), H, W, CHUNK_FRAMES, vol.device)
+    # Chunks in preparation beside the one integrating.  One file = one sequential bit stream = one warp at ~0.16
+    # instructions per cycle (ncu, profiles/decode_r02a.md): the GPU is nowhere near busy with one chunk's 2 x 256 warps,
+    # so throughput comes from the number of files in flight.
+    ahead = min(DECODE_AHEAD, len(chunks))
+    decs, pool_key = _acquire_decoders(min(ahead + 1, len(chunks)), H, W, CHUNK_FRAMES, vol.device)
     done = 0
     try:
         with ThreadPoolExecutor(max_workers=_decode_workers()) as pool, ThreadPoolExecutor(max_workers=ahead) as stage:
