@@ -62,7 +62,11 @@ __global__ void __launch_bounds__(32) png_inflate_kernel(const PngJob* __restric
     if (j.f.status != IC_OK) return;
     const int64_t cap = (int64_t)(j.f.rowbytes + 1) * j.f.height;
     int64_t got = 0;
-    int st = inflate_zlib(blob + j.f.z_off, j.f.z_len, raw + j.raw_off, cap, T, &got, (int)threadIdx.x, 32);
+    // The tables are addressed through a generic pointer the compiler cannot see through: with the __shared__ object itself
+    // it re-derived the shared-window base (S2R SR_CgaCtaId + LEA) for every symbol, 11 % of the kernel's stall samples.
+    InflateTables* Tp = &T;
+    asm volatile("" : "+l"(Tp));
+    int st = inflate_zlib(blob + j.f.z_off, j.f.z_len, raw + j.raw_off, cap, *Tp, &got, (int)threadIdx.x, 32);
     if (st == IC_OK && got != cap) st = IC_CORRUPT;              // libpng: "Not enough image data"
     if (threadIdx.x == 0) status[blockIdx.x] = st;
 }
