@@ -190,12 +190,12 @@ template <typename T>
 struct Pinned {                   // page-locked, grows geometrically
     T* p = nullptr;
     size_t cap = 0;
-    cudaError_t reserve(size_t n) {
+    cudaError_t reserve(size_t n, size_t want = 0) {              // need n elements; when growing, allocate `want` (>= n)
         if (n <= cap) return cudaSuccess;
         if (p) cudaFreeHost(p);
         p = nullptr;
         cap = 0;
-        const size_t want = std::max(n, n + n / 2);
+        want = std::max(want, n + n / 2);
         cudaError_t e = cudaHostAlloc((void**)&p, want * sizeof(T), cudaHostAllocDefault);
         if (e == cudaSuccess) cap = want;
         return e;
@@ -206,12 +206,12 @@ template <typename T>
 struct Device {
     T* p = nullptr;
     size_t cap = 0;
-    cudaError_t reserve(size_t n) {
+    cudaError_t reserve(size_t n, size_t want = 0) {
         if (n <= cap) return cudaSuccess;
         if (p) cudaFree(p);
         p = nullptr;
         cap = 0;
-        const size_t want = std::max(n, n + n / 4);
+        want = std::max(want, n + n / 4);
         cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
         if (e == cudaSuccess) cap = want;
         return e;
@@ -331,13 +331,14 @@ int decode_sources(otslam_decoder* d, int n, const Source* color, const Source* 
         }
     }
     const int n_png = (int)png_src.size(), n_jpg = (int)jpg_src.size();
-    OT_CUDA(d->h_zblob.reserve((size_t)ztotal + 16));
-    OT_CUDA(d->h_jblob.reserve((size_t)jtotal + 16));
-    OT_CUDA(d->h_jobs.reserve(std::max(1, n_png)));
-    OT_CUDA(d->h_frames.reserve(std::max(1, n_jpg)));
+    const size_t cap_jobs = (size_t)d->max_frames * 2;           // data-independent sizes: see the device buffers below
+    OT_CUDA(d->h_zblob.reserve((size_t)ztotal + 16, (size_t)ztotal * 2 + 16));
+    OT_CUDA(d->h_jblob.reserve((size_t)jtotal + 16, (size_t)jtotal * 2 + 16));
+    OT_CUDA(d->h_jobs.reserve(std::max(1, n_png), cap_jobs));
+    OT_CUDA(d->h_frames.reserve(std::max(1, n_jpg), (size_t)d->max_frames));
     OT_CUDA(d->h_tables.reserve(kMaxTableSets));
-    OT_CUDA(d->h_status.reserve((size_t)std::max(1, n_png + n_jpg)));
-    OT_CUDA(d->h_slots.reserve((size_t)std::max(1, n_jpg)));
+    OT_CUDA(d->h_status.reserve((size_t)std::max(1, n_png + n_jpg), cap_jobs));
+    OT_CUDA(d->h_slots.reserve((size_t)std::max(1, n_jpg), (size_t)d->max_frames));
 
     // ---- parse in parallel: PNG chunk walk + CRC + IDAT compaction; JPEG marker walk + scan copy
     std::vector<JpegHeader> jhdr((size_t)n_jpg);
@@ -408,16 +409,27 @@ int decode_sources(otslam_decoder* d, int n, const Source* color, const Source* 
         blk_total += f.n_blocks;
     }
 
-    OT_CUDA(d->d_zblob.reserve((size_t)ztotal + 16));
-    OT_CUDA(d->d_jblob.reserve((size_t)jtotal + 16));
-    OT_CUDA(d->d_raw.reserve((size_t)raw_total + 16));
-    OT_CUDA(d->d_coef.reserve((size_t)blk_total * 64 + 64));
-    OT_CUDA(d->d_samples.reserve((size_t)blk_total * 64 + 64));
-    OT_CUDA(d->d_jobs.reserve(std::max(1, n_png)));
-    OT_CUDA(d->d_frames.reserve(std::max(1, n_jpg)));
+    // Device buffers are sized by bounds that do not depend on the data -- (decoder's frame capacity) x (largest per-frame need
+    // seen) -- and the two compressed-byte areas (host and device) with 2x head room: a decoder that served a chunk of small
+    // files in one pass and a chunk of large ones in the next must not reallocate, because cudaFree / cudaFreeHost wait for
+    // every kernel on the device, including the other decoders' long-running entropy kernels.
+    int64_t raw_frame = 0, blk_frame = 0;
+    for (int k = 0; k < n_png; ++k)
+        if (d->h_jobs.p[k].f.status == IC_OK)
+            raw_frame = std::max<int64_t>(raw_frame, (((int64_t)(d->h_jobs.p[k].f.rowbytes + 1) * d->h_jobs.p[k].f.height) + 15) & ~15ll);
+    for (int q = 0; q < n_jpg; ++q)
+        if (d->h_frames.p[q].status == IC_OK) blk_frame = std::max<int64_t>(blk_frame, d->h_frames.p[q].n_blocks);
+    const size_t cap_frames = (size_t)d->max_frames * ((depth ? 1 : 0) + (color ? 1 : 0));      // >= n_png, >= n_jpg
+    OT_CUDA(d->d_zblob.reserve((size_t)ztotal + 16, (size_t)ztotal * 2 + 16));
+    OT_CUDA(d->d_jblob.reserve((size_t)jtotal + 16, (size_t)jtotal * 2 + 16));
+    OT_CUDA(d->d_raw.reserve((size_t)raw_total + 16, cap_frames * (size_t)raw_frame + 16));
+    OT_CUDA(d->d_coef.reserve((size_t)blk_total * 64 + 64, (size_t)d->max_frames * (size_t)blk_frame * 64 + 64));
+    OT_CUDA(d->d_samples.reserve((size_t)blk_total * 64 + 64, (size_t)d->max_frames * (size_t)blk_frame * 64 + 64));
+    OT_CUDA(d->d_jobs.reserve(std::max(1, n_png), cap_frames));
+    OT_CUDA(d->d_frames.reserve(std::max(1, n_jpg), (size_t)d->max_frames));
     OT_CUDA(d->d_tables.reserve(kMaxTableSets));
-    OT_CUDA(d->d_status.reserve((size_t)std::max(1, n_png + n_jpg)));
-    OT_CUDA(d->d_slots.reserve((size_t)std::max(1, n_jpg)));
+    OT_CUDA(d->d_status.reserve((size_t)std::max(1, n_png + n_jpg), cap_frames));
+    OT_CUDA(d->d_slots.reserve((size_t)std::max(1, n_jpg), (size_t)d->max_frames));
     if (depth) OT_CUDA(d->d_depth.reserve((size_t)d->max_frames * px));
     if (color) OT_CUDA(d->d_rgb.reserve((size_t)d->max_frames * px * 3));
 

@@ -15,7 +15,7 @@ import numpy as np
 from .o3d_compat import io as o3d_io
 
 CHUNK_FRAMES = 256
-DECODE_AHEAD = 3              # GPU decode: chunks being read / uploaded / decoded while one integrates
+DECODE_AHEAD = 4              # GPU decode: chunks being read / uploaded / decoded while one integrates
 _FMT = "[ScalableTSDFVolume::Integrate] Unsupported image format."
 
 
