@@ -269,6 +269,10 @@ int otslam_decoder_fetch(otslam_decoder* d, int first, int count, uint16_t* dept
  * object_ids nullable (multi-object arenas).  The slots' contents are consumed (holes are closed in place). */
 int otslam_decoder_integrate(otslam_decoder* d, otslam_volume* v, int n_keep, const int32_t* slots, const double intr[4],
                              const double* extrinsics, double depth_scale, double depth_trunc, const int32_t* object_ids);
+/* np.loadtxt(pose_path) (reconstruct_rgbd.py:92) for n pose files at once (host threads; no GPU involved): poses[n][16]
+ * row-major.  status 0 = 16 plain decimal numbers, converted with correctly rounded strtod (the same doubles np.loadtxt
+ * yields); 1 = anything else (comments, commas, other counts, inf / nan ...): parse it with np.loadtxt; 2 = unreadable. */
+int otslam_read_pose_files(int n, const char* const* paths, double* poses, int32_t* status);
 /* device times (CUDA events, ms) of the last decode: [0] inflate, [1] PNG filters + emit, [2] JPEG Huffman, [3] IDCT,
  * [4] upsampling + colour; [5] = compressed bytes uploaded */
 int otslam_decoder_profile(otslam_decoder* d, double out[6]);

@@ -89,6 +89,7 @@ _SIGS = {
     "otslam_decoder_fetch": (_i, [_vp, _i, _i, _vp, _vp]),
     "otslam_decoder_integrate": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _d, _d, _vp]),
     "otslam_decoder_profile": (_i, [_vp, _vp]),
+    "otslam_read_pose_files": (_i, [_i, _vp, _vp, _vp]),
 }
 EXPORTS = tuple(_SIGS)
 MISSING = []                        # tests assert this is empty: the .so must export the whole header

@@ -18,6 +18,7 @@
 // All arithmetic lives in imgcodec_core.h as __host__ __device__ functions, checked bit for bit against OpenCV's
 // libpng / libjpeg-turbo on the CPU (tests/test_imgcodec_model.py) and on the GPU (tests/test_gpu_decode.py).
 #include <fcntl.h>
+#include <locale.h>
 #include <sched.h>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -639,6 +640,63 @@ int otslam_decoder_integrate(otslam_decoder* d, otslam_volume* v, int n_keep, co
                                                      depth_scale, depth_trunc, OTSLAM_MEM_DEVICE);
     return otslam_volume_integrate_batch(v, n_keep, d->d_depth.p, d->d_rgb.p, d->W, d->H, intr, extrinsics, depth_scale, depth_trunc,
                                          OTSLAM_MEM_DEVICE);
+}
+
+// np.loadtxt(pose_path) for the 4x4 text files of a capture tree.  Accepts exactly what the Python fast path accepts
+// (pipeline.read_pose: 16 whitespace-separated plain decimal numbers, no comments, no commas) and converts with the C-locale
+// strtod, which -- like Python's float() -- is correctly rounded, so the doubles are the same bits; everything else is left
+// to np.loadtxt (status 1).  Host threads, no GPU involved: 16 interpreter threads parsing poses contended for the GIL and
+// took 160 us per file, six times the single-threaded cost.
+int otslam_read_pose_files(int n, const char* const* paths, double* poses, int32_t* status) {
+    if (n < 0 || (n && (!paths || !poses || !status))) return set_error(OTSLAM_ERR_INVALID, "read_pose_files: bad arguments");
+    static locale_t c_locale = newlocale(LC_ALL_MASK, "C", (locale_t)0);
+    parallel_for(n, [&](int i) {
+        status[i] = 2;
+        for (int k = 0; k < 16; ++k) poses[(size_t)i * 16 + k] = 0.0;
+        std::vector<uint8_t> buf;
+        if (!read_file(paths[i], buf)) return;
+        status[i] = 1;
+        if (buf.size() > 16384) return;
+        buf.push_back(0);
+        const char* p = reinterpret_cast<const char*>(buf.data());
+        const char* end = p + buf.size() - 1;
+        double v[16];
+        int cnt = 0;
+        while (p < end) {
+            const unsigned char c = (unsigned char)*p;
+            if (c == ' ' || (c >= 9 && c <= 13)) { ++p; continue; }
+            if (cnt == 16) return;                                           // a 17th token
+            // [+-]? ( digits [. digits*] | . digits ) ( [eE] [+-]? digits )?
+            const char* q = p;
+            if (*q == '+' || *q == '-') ++q;
+            int nd = 0;
+            while (*q >= '0' && *q <= '9') { ++q; ++nd; }
+            if (*q == '.') {
+                ++q;
+                while (*q >= '0' && *q <= '9') { ++q; ++nd; }
+            }
+            if (nd == 0) return;
+            if (*q == 'e' || *q == 'E') {
+                ++q;
+                if (*q == '+' || *q == '-') ++q;
+                int ne = 0;
+                while (*q >= '0' && *q <= '9') { ++q; ++ne; }
+                if (ne == 0) return;
+            }
+            const unsigned char t = (unsigned char)*q;
+            if (!(q == end || t == ' ' || (t >= 9 && t <= 13))) return;      // anything else glued to the number (or a NUL inside the file)
+            if (q - p > 1024) return;
+            char* stop = nullptr;
+            v[cnt] = c_locale ? strtod_l(p, &stop, c_locale) : strtod(p, &stop);
+            if (stop != q) return;
+            ++cnt;
+            p = q;
+        }
+        if (cnt != 16) return;
+        for (int k = 0; k < 16; ++k) poses[(size_t)i * 16 + k] = v[k];
+        status[i] = 0;
+    });
+    return OTSLAM_OK;
 }
 
 int otslam_decoder_profile(otslam_decoder* d, double out_ms[6]) {

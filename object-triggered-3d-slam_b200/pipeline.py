@@ -61,6 +61,20 @@ def read_pose(path):
     return np.loadtxt(path)
 
 
+def read_poses(paths):
+    """read_pose for many files at once through the library's host threads (otslam_read_pose_files: no interpreter time per
+    file).  Returns (poses [n,4,4] f64, status [n] i32); status != 0 = not the plain 16-number text: use read_pose."""
+    import ctypes as C
+    from . import _lib
+    n = len(paths)
+    poses = np.zeros((n, 4, 4), np.float64)
+    status = np.ones(n, np.int32)
+    if n:
+        arr = (C.c_char_p * n)(*[os.fsencode(p) for p in paths])
+        _lib.check(_lib.lib.otslam_read_pose_files(n, arr, _lib.ptr(poses), _lib.ptr(status)))
+    return poses, status
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # Raw side-car of a capture tree (SURVEY 8f row 1, "streaming ingest"): JPEG / PNG decoding is what bounds the drop-in
 # scripts end to end (~1.8 k frames/s on 16 host threads against ~50 k frames/s of GPU integration).  With
@@ -239,11 +253,18 @@ def _integrate_files_gpu(volume, triples, intrinsics, T_fix, depth_scale, depth_
     done = 0
     try:
         with ThreadPoolExecutor(max_workers=_decode_workers()) as pool, ThreadPoolExecutor(max_workers=ahead) as stage:
-            def pose(k, chunk):
-                try:
-                    return np.linalg.inv(read_pose(chunk[k][2]) @ T_fix), None
-                except Exception as err:  # noqa: BLE001
-                    return None, err
+            def extrinsics(chunk):
+                """extrinsic of every frame of a chunk with the host loop's arithmetic (inv(pose @ T_fix), frame by frame);
+                the text files are parsed by the library's threads -- a pool of interpreter threads doing it contended for
+                the GIL (160 us per file instead of 27) and was what bounded the loop"""
+                poses, pstat = read_poses([t[2] for t in chunk])
+                out = []
+                for k in range(len(chunk)):
+                    try:
+                        out.append((np.linalg.inv((poses[k] if pstat[k] == 0 else read_pose(chunk[k][2])) @ T_fix), None))
+                    except Exception as err:  # noqa: BLE001
+                        out.append((None, err))
+                return out
 
             def stock(k, chunk, dec):
                 """the reference's per-frame body on the host for a frame the GPU decoders passed on"""
@@ -255,13 +276,16 @@ def _integrate_files_gpu(volume, triples, intrinsics, T_fix, depth_scale, depth_
 
             def prepare(ci):
                 dec, chunk = decs[ci % len(decs)], chunks[ci]
-                poses = [pool.submit(pose, k, chunk) for k in range(len(chunk))]         # parsed while the call below decodes
+                exts = pool.submit(extrinsics, chunk)                                     # while the call below decodes
                 cstat, dstat = dec.decode_files([t[0] for t in chunk], [t[1] for t in chunk])
                 prof = dec.profile()
                 prof["frames"], prof["passed_on"] = len(chunk), int(np.count_nonzero(cstat | dstat))
                 last_decode_profile.append(prof)
-                redo = {k: pool.submit(stock, k, chunk, dec) for k in np.nonzero(cstat | dstat)[0]}
-                return [(redo[k] if k in redo else poses[k]).result() for k in range(len(chunk))]
+                redo = {int(k): pool.submit(stock, int(k), chunk, dec) for k in np.nonzero(cstat | dstat)[0]}
+                res = exts.result()
+                for k, f in redo.items():
+                    res[k] = f.result()
+                return res
 
             futs = {ci: stage.submit(prepare, ci) for ci in range(ahead)}
             for ci, chunk in enumerate(chunks):

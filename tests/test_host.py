@@ -206,6 +206,44 @@ def test_read_pose_equals_loadtxt(tmp_path):
         pipeline.read_pose(str(tmp_path / "missing.txt"))
 
 
+def test_read_poses_library_reader_equals_loadtxt(tmp_path):
+    """otslam_read_pose_files (the GPU-decode loop's pose reader: host threads of the library, no interpreter time per file)
+    gives np.loadtxt's bits for plain 16-number files and hands everything else back (status 1 / 2)."""
+    from otslam_b200 import capture
+    rng = np.random.default_rng(1)
+    paths, want = [], []
+    for k in range(120):
+        T = rng.normal(size=(4, 4)) * 10.0 ** rng.integers(-8, 9)
+        if k % 10 == 0:
+            T.flat[rng.integers(0, 16)] = [0.0, -0.0, 1e-320, 1.7976931348623157e308, 5e-324][k // 10 % 5]
+        p = tmp_path / f"p{k}.txt"
+        if k % 4 == 0:
+            p.write_text(capture.pose_text(T))
+        elif k % 4 == 1:
+            np.savetxt(p, T)
+        elif k % 4 == 2:
+            p.write_text("\n".join(" ".join(repr(float(x)) for x in r) for r in T) + "\n")
+        else:
+            p.write_text("\t".join(f"{x:+.17g}" for x in T.ravel()) + "\r\n")      # one line, tabs, explicit signs, CRLF
+        paths.append(str(p)); want.append(np.loadtxt(str(p)).reshape(4, 4))
+    poses, status = pipeline.read_poses(paths)
+    assert (status == 0).all()
+    assert (poses.view(np.int64) == np.stack(want).view(np.int64)).all()
+    odd = {"comment": "# pose\n" + capture.pose_text(np.eye(4)), "commas": ",".join(["1.0"] * 16), "fifteen": " ".join(["1.0"] * 15),
+           "seventeen": " ".join(["1.0"] * 17), "inf": " ".join(["inf"] * 16), "hex": " ".join(["0x1p3"] * 16),
+           "glued": " ".join(["1.0x"] * 16), "underscore": " ".join(["1_0.0"] * 16), "empty": "", "exp": " ".join(["1e"] * 16),
+           "nul": " ".join(["1.0"] * 15) + " 1.0\0 2.0"}
+    op = []
+    for name, txt in odd.items():
+        q = tmp_path / f"{name}.txt"
+        q.write_bytes(txt.encode())
+        op.append(str(q))
+    op.append(str(tmp_path / "missing.txt"))
+    poses, status = pipeline.read_poses(op)
+    assert list(status) == [1] * len(odd) + [2]
+    assert pipeline.read_poses([])[1].shape == (0,)
+
+
 def test_synth_matches_capture_contract():
     seq = synth.make_sequence("table", 300, subsample=(0, 150))
     d, c = seq.numpy()
@@ -338,3 +376,101 @@ def test_raw_sidecar_round_trip_and_invalidation(tmp_path, monkeypatch):
     d3, c3 = np.zeros_like(d0), np.zeros_like(c0)
     _, err = pipeline._decode_into(t, intr, synth.T_FIX, d3, c3)
     assert err is None and len(calls) == 2 and (d3 == d0).all()
+
+
+def test_gpu_decode_file_loop_orchestration(tmp_path, monkeypatch):
+    """pipeline._integrate_files_gpu with stand-in decoders (no GPU): DECODE_AHEAD chunks are prepared concurrently beside
+    the one integrating, a decoder is never handed a new chunk before its previous chunk has been integrated, frames reach
+    the volume exactly once in file order, frames the decoders pass on go through the stock decoder and are `put` back,
+    and the print-and-skip / abort semantics are the host loop's."""
+    import threading
+    import time
+    intr = o3d.camera.PinholeCameraIntrinsic(64, 48, 56.0, 56.0, 32.5, 24.5)
+    seq = synth.make_sequence("table", 23, intr=(64, 48, 56.0, 56.0, 32.5, 24.5))
+    base = str(tmp_path / "scan")
+    synth.write_capture_tree(seq, base)
+    monkeypatch.setattr(pipeline, "CHUNK_FRAMES", 4)
+    monkeypatch.setattr(pipeline, "DECODE_AHEAD", 2)
+
+    def triple(i, ok=True):
+        return (os.path.join(base, "color", f"Object_0_{i}.jpg"),
+                os.path.join(base, "depth", f"Object_0_{i}.png" if ok else "missing.png"),
+                os.path.join(base, "poses", f"Object_0_{i}.txt"), i)
+
+    passed_on = {2, 9, 14}                                       # status 1: valid files the GPU decoders do not cover
+    missing = {6, 19}                                            # status 2 -> the stock path raises the reference's error
+    triples = [triple(i, ok=(i not in missing)) for i in range(1, 24)]
+    lock = threading.Lock()
+    state = {"preparing": 0, "max_preparing": 0, "log": []}
+
+    class FakeDecoder:
+        def __init__(self, name):
+            self.name, self.busy, self.loaded, self.puts = name, False, None, []
+
+        def decode_files(self, cps, dps):
+            with lock:
+                assert not self.busy and self.loaded is None, "decoder reused before its chunk was integrated"
+                self.busy = True
+                state["preparing"] += 1
+                state["max_preparing"] = max(state["max_preparing"], state["preparing"])
+            time.sleep(0.05)                                     # the library call (GIL released)
+            labels = [int(os.path.basename(p).split("_")[-1].split(".")[0]) for p in cps]
+            cs = np.array([1 if l in passed_on else 0 for l in labels], np.int32)
+            ds = np.array([2 if "missing" in d else 0 for d in dps], np.int32)
+            with lock:
+                self.busy, self.loaded = False, labels
+                state["preparing"] -= 1
+            return cs, ds
+
+        def profile(self):
+            return {"compressed_bytes": 0}
+
+        def put(self, slot, depth, rgb):
+            assert depth.shape == (48, 64) and rgb.shape == (48, 64, 3)
+            self.puts.append(self.loaded[slot])
+
+        def integrate(self, vol, slots, k, exts, depth_scale, depth_trunc):
+            with lock:
+                assert self.loaded is not None and not self.busy
+                state["log"].append((self.name, [self.loaded[s] for s in slots], np.array(exts)))
+                self.loaded = None
+            time.sleep(0.01)
+
+        def close(self):
+            pass
+
+    fakes = []
+
+    def acquire(count, h, w, frames, device):
+        assert (h, w, frames) == (48, 64, 4) and count == 3      # DECODE_AHEAD + 1
+        fakes[:] = [FakeDecoder(i) for i in range(count)]
+        pipeline._decoder_lock = pipeline._decoder_lock or threading.Lock()
+        return list(fakes), ("fake", len(fakes))
+
+    monkeypatch.setattr(pipeline, "_acquire_decoders", acquire)
+
+    class Vol:
+        class _vol:
+            device = 0
+
+    errs, prog = [], []
+    n = pipeline._integrate_files_gpu(Vol, triples, intr, synth.T_FIX, 1000.0, 3.0, True, lambda l, i, t: prog.append(l),
+                                      lambda l, e: errs.append((l, str(e))))
+    pipeline._decoder_pool.pop(("fake", 3), None)
+    good = [i for i in range(1, 24) if i not in missing]
+    assert n == len(good) and [l for l, _ in errs] == sorted(missing) and prog == good
+    assert all("Unsupported image format" in m for _, m in errs)
+    assert [l for _, labels, _ in state["log"] for l in labels] == good                 # file order, each frame once
+    assert [name for name, _, _ in state["log"]] == [0, 1, 2, 0, 1, 2]                  # six chunks round-robin over 3 decoders
+    assert state["max_preparing"] == 2                                                   # two chunks in flight beside the integration
+    assert sorted(l for f in fakes for l in f.puts) == sorted(passed_on)                 # stock-decoded frames went back into their slots
+    want = [np.linalg.inv(np.loadtxt(triple(i)[2]) @ synth.T_FIX) for i in good]
+    got = [e for _, _, exts in state["log"] for e in exts]
+    assert all((a == b).all() for a, b in zip(got, want))
+    assert len(pipeline.last_decode_profile) == 6 and sum(c["passed_on"] for c in pipeline.last_decode_profile) == 5
+    # abort semantics: the first bad frame (6, in chunk 1) raises; chunk 0 has been integrated, nothing after it
+    state["log"].clear()
+    with pytest.raises(RuntimeError, match="Unsupported image format"):
+        pipeline._integrate_files_gpu(Vol, triples, intr, synth.T_FIX, 1000.0, 3.0, False, None, None)
+    pipeline._decoder_pool.pop(("fake", 3), None)
+    assert [labels for _, labels, _ in state["log"]] == [[1, 2, 3, 4]]
