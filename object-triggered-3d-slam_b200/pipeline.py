@@ -2,8 +2,9 @@
 
 The reference integrates frame by frame (/root/reference/3d_model/reconstruct_rgbd.py:86-109:
 read colour, read depth, loadtxt pose, pose @ T_fix, inv, create_from_color_and_depth, integrate).
-Here the files are decoded on the host in chunks and each chunk goes to the GPU in ONE
-`integrate_sequence` call (frame order preserved, up to 32 frames fused per block residency);
+Here the files are handled in chunks: their compressed bytes are uploaded and decoded on the GPU (decoder.py; or decoded by
+OpenCV threads on the host, OTSLAM_GPU_DECODE=0) and each chunk is integrated in ONE call (frame order preserved, up to
+32 frames fused per block residency);
 per-frame failures keep the reference's semantics: abort (reconstruct_rgbd.py, no try) or
 print-and-skip (reconstruct_rgbd_filter.py:108-109, multi_reconstruct_rgbd_filter.py:102-103).
 """
@@ -236,7 +237,7 @@ def _integrate_files_gpu(volume, triples, intrinsics, T_fix, depth_scale, depth_
     """integrate_files with the decoders on the GPU (decoder.py): a chunk's files are read by the library's host threads,
     the compressed bytes are uploaded and decoded in HBM, and the decoded slots go straight into the volume.  DECODE_AHEAD
     chunks are in preparation (read + upload + decode: one worker thread and one decoder with its own streams each) while
-    another integrates; the pose files are parsed by the thread pool while the library call decodes.  Frames the GPU decoders pass on
+    another integrates; the pose files are parsed by the library's host threads (read_poses) meanwhile.  Frames the GPU decoders pass on
     (status != 0: progressive JPEG, another size, a damaged or missing file ...) go through the stock decoders exactly as in
     the host path, so warnings, exceptions and skip semantics are the host path's."""
     from concurrent.futures import ThreadPoolExecutor
@@ -321,7 +322,11 @@ def integrate_files(volume, triples, intrinsics, T_fix, depth_scale=1000.0, dept
     GIL) straight into pooled chunk buffers, and chunk k+1 is decoded while the GPU integrates chunk k (the
     C-ABI call releases the GIL as well).  Results are consumed in file order, so the per-frame semantics -- abort
     on the first bad frame, or print-and-skip -- and the frame order seen by the volume are exactly the
-    sequential loop's."""
+    sequential loop's.
+
+    Default (OTSLAM_GPU_DECODE unset or 1, a plain volume, no side-car): the decoding itself runs on the GPU as well --
+    _integrate_files_gpu above; the host-decode loop below remains for OTSLAM_GPU_DECODE=0, for the raw side-car and
+    for volumes that are objects of a multi-object arena."""
     from concurrent.futures import ThreadPoolExecutor
     from .volume import TSDFVolume
     done = 0
