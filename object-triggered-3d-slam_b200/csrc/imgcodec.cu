@@ -403,6 +403,8 @@ int decode_sources(otslam_decoder* d, int n, const Source* color, const Source* 
             for (int t = 0; t < 4; ++t)
                 for (int k = 0; k < 64; ++k) T.q[t][k] = hd.q[t][k];
             if (!ok) { f.status = IC_CORRUPT; continue; }           // libjpeg: "Bogus Huffman table definition"
+            for (int a = 0; a < 2; ++a)
+                if (hd.h_set[2 + a]) jpeg_build_acfast(T.h[2 + a], T.acfast[a]);
             it = sets.emplace(std::move(key), n_sets++).first;
         }
         f.tables = it->second;

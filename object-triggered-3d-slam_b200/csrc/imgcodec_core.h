@@ -450,6 +450,10 @@ struct JpegHuffTable {
 struct JpegTables {               // one per distinct (DHT, DQT) content of a batch; nearly always one per batch
     JpegHuffTable h[4];           // dc0, dc1, ac0, ac1
     uint16_t q[4][64];            // quantisation tables, zig-zag order as stored in the file
+    // AC symbols whose code AND value bits fit the lookahead window, resolved by one load: bits 0-4 = bits consumed
+    // (code + value), bits 5-10 = positions to skip first, bits 16-31 = the coefficient (int16); 0 = take the two-step
+    // path.  End-of-block is "skip 63" (leaves the block), ZRL is "skip 15, store 0" (the block is pre-zeroed).
+    uint32_t acfast[2][1 << kJLook];
 };
 struct JpegFrame {
     int32_t status;
@@ -578,8 +582,17 @@ IC_FN inline int jpeg_decode_scan(const JpegFrame& f, const JpegTables& T, const
                             pred[c] += jpeg_extend(r, s);
                         }
                         blk[0] = (int16_t)pred[c];
+                        const uint32_t* acfast = T.acfast[f.ta[c]];
                         for (int k = 1; k < 64;) {
                             b.refill();
+                            const uint32_t e = acfast[(uint32_t)(b.buf >> (64 - kJLook))];
+                            if (e) {                                // run, size and value from one lookup
+                                k += (int)((e >> 5) & 63u);
+                                if (k < 64) blk[k] = (int16_t)(e >> 16);
+                                ++k;
+                                b.drop((int)(e & 31u));
+                                continue;
+                            }
                             int rs = jpeg_huff_decode(b, ac);
                             if (rs < 0) rs = 0;
                             const int r = rs >> 4;
@@ -834,6 +847,24 @@ inline bool jpeg_build_huff(const uint8_t bits[16], const uint8_t* vals, int nva
     }
     t.maxcode[17] = 0xFFFFF;
     return k == nvals;
+}
+
+// the one-lookup table of an AC Huffman table (JpegTables::acfast)
+inline void jpeg_build_acfast(const JpegHuffTable& ac, uint32_t* out) {
+    for (uint32_t peek = 0; peek < (1u << kJLook); ++peek) {
+        out[peek] = 0;
+        const uint32_t e = ac.look[peek];
+        if (!e) continue;
+        const int len = (int)(e >> 8), r = (int)((e & 255u) >> 4), sz = (int)(e & 15u);
+        if (sz == 0) {
+            out[peek] = (uint32_t)len | ((r == 15 ? 15u : 63u) << 5);
+            continue;
+        }
+        if (len + sz > kJLook) continue;
+        const int extra = (int)((peek >> (kJLook - len - sz)) & ((1u << sz) - 1u));
+        const int val = jpeg_extend(extra, sz);
+        out[peek] = (uint32_t)(len + sz) | ((uint32_t)r << 5) | ((uint32_t)(uint16_t)(int16_t)val << 16);
+    }
 }
 
 struct JpegHeader {               // raw table bytes of one file: the batch decoder de-duplicates them into JpegTables sets

@@ -85,6 +85,8 @@ extern "C" int model_decode_jpeg(const uint8_t* file, int64_t size, int H, int W
     for (int t = 0; t < 4; ++t)
         for (int k = 0; k < 64; ++k) T->q[t][k] = hd.q[t][k];
     if (!ok) { delete T; return IC_CORRUPT; }
+    for (int a = 0; a < 2; ++a)
+        if (hd.h_set[2 + a]) jpeg_build_acfast(T->h[2 + a], T->acfast[a]);
     std::vector<int16_t> coef((size_t)f.n_blocks * 64, 0);
     std::vector<uint8_t> samples((size_t)f.n_blocks * 64);
     f.blk_off = 0;
