@@ -67,7 +67,9 @@ __global__ void __launch_bounds__(32) png_inflate_kernel(const PngJob* __restric
     // it re-derived the shared-window base (S2R SR_CgaCtaId + LEA) for every symbol, 11 % of the kernel's stall samples.
     InflateTables* Tp = &T;
     asm volatile("" : "+l"(Tp));
-    int st = inflate_zlib(blob + j.f.z_off, j.f.z_len, raw + j.raw_off, cap, *Tp, &got, (int)threadIdx.x, 32);
+    uint8_t* out = raw + j.raw_off;                               // likewise kept in registers instead of being re-derived from
+    asm volatile("" : "+l"(out));                                 // the kernel parameters at every store
+    int st = inflate_zlib(blob + j.f.z_off, j.f.z_len, out, cap, *Tp, &got, (int)threadIdx.x, 32);
     if (st == IC_OK && got != cap) st = IC_CORRUPT;              // libpng: "Not enough image data"
     if (threadIdx.x == 0) status[blockIdx.x] = st;
 }

@@ -171,21 +171,39 @@ IC_FN inline int huff_decode(BitsLSB& b, const uint16_t* fast, int fast_bits, co
 IC_FN inline int inflate_codes(BitsLSB& b, uint8_t* out, int64_t& pos64, int64_t cap64, const InflateTables& T, bool& full, int lane,
                                int nlanes) {
     // The loop is tuned for literals (98 % of the symbols of sensor-like depth, ncu profiles/decode_r02a.md): one table
-    // load and one compare recognise "a literal whose code fits the fast table"; the input-underrun test is left to the
-    // paths that end a run of literals (a run is bounded by `cap` in any case).  The write position is a pointer kept in
-    // registers, 32-bit offsets elsewhere (an image's scan lines are < 2^31 bytes: the decoder object caps height x width).
+    // load and one compare recognise "a literal whose code fits the fast table", and one refill (> 32 bits) feeds up to
+    // three of them (<= 10 bits each) without further refill or bounds tests.  The input-underrun test is left to the
+    // paths that end a run of literals (a run is bounded by `cap` in any case).  32-bit positions (an image's scan lines
+    // are < 2^31 bytes: the decoder object caps height x width).
     const uint16_t* const lit_fast = T.lit_fast;
-    uint8_t* wp = out + pos64;
-    uint8_t* const wend = out + cap64;
+    const uint32_t fmask = (1u << kLitFast) - 1u;
+    int pos = (int)pos64;
+    const int cap = (int)cap64;
     int status = IC_OK;
     for (;;) {
         b.refill();
-        const uint32_t e = lit_fast[(uint32_t)b.buf & ((1u << kLitFast) - 1u)];
+        uint32_t e = lit_fast[(uint32_t)b.buf & fmask];
         if (e - 1u < (256u << 4) - 1u) {                     // 1 <= e < 4096: fast entry, symbol < 256
-            if (wp >= wend) { full = true; break; }
+            if (pos + 3 > cap) {                             // the last bytes of the image: one at a time
+                if (pos >= cap) { full = true; break; }
+                b.drop((int)(e & 15u));
+                if (lane == 0) out[pos] = (uint8_t)(e >> 4);
+                ++pos;
+                continue;
+            }
             b.drop((int)(e & 15u));
-            if (lane == 0) *wp = (uint8_t)(e >> 4);
-            ++wp;
+            if (lane == 0) out[pos] = (uint8_t)(e >> 4);
+            ++pos;
+            e = lit_fast[(uint32_t)b.buf & fmask];
+            if (e - 1u >= (256u << 4) - 1u) continue;        // not a short literal: start over (refill, general path)
+            b.drop((int)(e & 15u));
+            if (lane == 0) out[pos] = (uint8_t)(e >> 4);
+            ++pos;
+            e = lit_fast[(uint32_t)b.buf & fmask];
+            if (e - 1u >= (256u << 4) - 1u) continue;
+            b.drop((int)(e & 15u));
+            if (lane == 0) out[pos] = (uint8_t)(e >> 4);
+            ++pos;
             continue;
         }
         int sym;
@@ -197,9 +215,9 @@ IC_FN inline int inflate_codes(BitsLSB& b, uint8_t* out, int64_t& pos64, int64_t
         }
         if (sym < 0 || b.cnt < 0) { status = IC_CORRUPT; break; }
         if (sym < 256) {                                     // a literal with a long code
-            if (wp >= wend) { full = true; break; }
-            if (lane == 0) *wp = (uint8_t)sym;
-            ++wp;
+            if (pos >= cap) { full = true; break; }
+            if (lane == 0) out[pos] = (uint8_t)sym;
+            ++pos;
             continue;
         }
         if (sym == 256) break;
@@ -221,20 +239,21 @@ IC_FN inline int inflate_codes(BitsLSB& b, uint8_t* out, int64_t& pos64, int64_t
             const int eb = (ds >> 1) - 1;
             dist = 1 + ((2 + (ds & 1)) << eb) + (int)b.bits(eb);
         }
-        if (b.cnt < 0 || dist > wp - out) { status = IC_CORRUPT; break; }
-        if (len > wend - wp) { len = (int)(wend - wp); full = true; }
-        const uint8_t* src = wp - dist;
-        IC_TEAM_SYNC();                                      // everything before `wp` is written, by whichever lane
+        if (b.cnt < 0 || dist > pos) { status = IC_CORRUPT; break; }
+        if (len > cap - pos) { len = cap - pos; full = true; }
+        uint8_t* dst = out + pos;
+        const uint8_t* src = dst - dist;
+        IC_TEAM_SYNC();                                      // everything before `pos` is written, by whichever lane
         if (dist >= len) {
-            for (int i = lane; i < len; i += nlanes) wp[i] = src[i];
+            for (int i = lane; i < len; i += nlanes) dst[i] = src[i];
         } else {                                             // the match overlaps itself: the last `dist` bytes repeat
-            for (int i = lane; i < len; i += nlanes) wp[i] = src[i % dist];
+            for (int i = lane; i < len; i += nlanes) dst[i] = src[i % dist];
         }
-        wp += len;
+        pos += len;
         if (full) break;
     }
     if (b.cnt < 0) status = IC_CORRUPT;                      // the stream ended inside a run of literals
-    pos64 = wp - out;
+    pos64 = pos;
     return status;
 }
 
