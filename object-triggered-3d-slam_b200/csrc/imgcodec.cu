@@ -16,7 +16,7 @@
 // A single file's entropy decoding is inherently sequential; the parallelism is across the files of a chunk (hundreds of
 // independent bit streams, one per warp, latency-bound) -- which is the batch-of-frames shape the frame loop already has.
 // All arithmetic lives in imgcodec_core.h as __host__ __device__ functions, checked bit for bit against OpenCV's
-// libpng / libjpeg-turbo on the CPU (tests/test_imgcodec_model.py) and on the GPU (tests/test_gpu_decode.py).
+// libpng / libjpeg-turbo on the CPU (tests/test_imgcodec_model.py) and on the GPU (tests/test_gpu_zz_decode.py).
 #include <fcntl.h>
 #include <locale.h>
 #include <sched.h>

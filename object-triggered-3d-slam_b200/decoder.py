@@ -5,7 +5,7 @@ libpng on one core.  FrameDecoder hands a chunk of files (paths, or bytes alread
 `otslam_decoder_decode_files` / `otslam_decoder_decode`: host threads only read and frame the files, the compressed bytes
 cross PCIe, and inflate / PNG filters / Huffman / IDCT / upsampling / colour conversion run on the GPU into frame slots
 that `integrate` feeds to the volume without a host round trip.  Pixels equal the stock decoders' bit for bit
-(tests/test_imgcodec_model.py on the CPU, tests/test_gpu_decode.py on the GPU)."""
+(tests/test_imgcodec_model.py on the CPU, tests/test_gpu_zz_decode.py on the GPU)."""
 import ctypes as C
 import os
 

@@ -4,7 +4,7 @@
 # of the inflate kernel.
 # Usage: /usr/local/graft/bin/gpurun --timeout 600 -- 'bash tools/decode_check.sh <tag>'
 tag=${1:-dec}
-timeout 200 python -m pytest tests/test_gpu_decode.py tests/test_gpu_scripts.py -x -q --tb=short 2>&1 | tail -8
+timeout 200 python -m pytest tests/test_gpu_zz_decode.py tests/test_gpu_scripts.py -x -q --tb=short 2>&1 | tail -8
 timeout 300 python bench.py > gpurun_out/${tag}_n1.json 2> gpurun_out/${tag}_n1.err
 python - <<PY
 import json
