@@ -243,7 +243,7 @@ int otslam_grid_smart_paste(uint8_t* base, const uint8_t* overlay, int width, in
                             int unknown_pixel, int threshold, int device);
 
 /* ---- the readers in front of the frame loop.  o3d.io.read_image(color_path) and
- * o3d.io.read_image(depth_path) (3d_model/reconstruct_rgbd.py:90-91, reconstruct_rgbd_filter.py:88-89) decode the files
+ * o3d.io.read_image(depth_path) (3d_model/reconstruct_rgbd.py:88-89, reconstruct_rgbd_filter.py:91-92) decode the files
  * ScannerNode::save_files wrote with cv::imwrite (ros2_ws/src/system_manager/src/scanner_node.cpp:268-283: baseline JPEG
  * colour, 16-bit grey PNG depth; the gt_ / plain capture tools write 8-bit RGB PNG colour).  A decoder object takes a chunk of
  * such files -- as paths or as bytes already in memory --, uploads the COMPRESSED bytes and runs inflate / PNG filters /
@@ -265,11 +265,11 @@ int otslam_decoder_decode(otslam_decoder* d, int n, const uint8_t* color_blob, c
 int otslam_decoder_put(otslam_decoder* d, int slot, const uint16_t* depth, const uint8_t* rgb);
 /* copy slots [first, first + count) out (host or device pointers; either nullable) */
 int otslam_decoder_fetch(otslam_decoder* d, int first, int count, uint16_t* depth, uint8_t* rgb);
-/* volume.integrate(rgbd, intrinsic, extrinsic) (reconstruct_rgbd.py:106-109) for the slots listed (ascending), in that order;
+/* volume.integrate(rgbd, intrinsic, extrinsic) (reconstruct_rgbd.py:99-107) for the slots listed (ascending), in that order;
  * object_ids nullable (multi-object arenas).  The slots' contents are consumed (holes are closed in place). */
 int otslam_decoder_integrate(otslam_decoder* d, otslam_volume* v, int n_keep, const int32_t* slots, const double intr[4],
                              const double* extrinsics, double depth_scale, double depth_trunc, const int32_t* object_ids);
-/* np.loadtxt(pose_path) (reconstruct_rgbd.py:92) for n pose files at once (host threads; no GPU involved): poses[n][16]
+/* np.loadtxt(pose_path) (reconstruct_rgbd.py:90) for n pose files at once (host threads; no GPU involved): poses[n][16]
  * row-major.  status 0 = 16 plain decimal numbers, converted with correctly rounded strtod (the same doubles np.loadtxt
  * yields); 1 = anything else (comments, commas, other counts, inf / nan ...): parse it with np.loadtxt; 2 = unreadable. */
 int otslam_read_pose_files(int n, const char* const* paths, double* poses, int32_t* status);

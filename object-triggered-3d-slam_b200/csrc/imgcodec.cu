@@ -1,6 +1,6 @@
 // imgcodec.cu -- capture files -> frames in HBM without the host touching a pixel (second half).
 //
-// The reference reads every frame pair with o3d.io.read_image (/root/reference/3d_model/reconstruct_rgbd.py:90-91): libjpeg
+// The reference reads every frame pair with o3d.io.read_image (/root/reference/3d_model/reconstruct_rgbd.py:88-89): libjpeg
 // and libpng on one CPU core, ~6 ms per pair -- 100x the GPU's integration time for the same frame.  Here a chunk of files is
 // read by host threads (I/O only: chunk / marker walking, CRC), the COMPRESSED bytes cross PCIe (a 640x480 pair is ~130-400 KB
 // instead of 1.5 MB raw), and the arithmetic of both decoders runs on the GPU:

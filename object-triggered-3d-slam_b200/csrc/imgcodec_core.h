@@ -2,7 +2,7 @@
 // __host__ __device__ code: depth = 16-bit grey PNG, colour = baseline JPEG (or 8-bit RGB / RGBA PNG for the gt_ / plain
 // capture tools), the bytes ScannerNode::save_files produces with cv::imwrite
 // (/root/reference/ros2_ws/src/system_manager/src/scanner_node.cpp:268-283) and the reference reads back with
-// o3d.io.read_image (/root/reference/3d_model/reconstruct_rgbd.py:90-91).
+// o3d.io.read_image (/root/reference/3d_model/reconstruct_rgbd.py:88-89).
 //
 // The kernels in imgcodec.cu are thin wrappers around these functions; tests/imgcodec_model.cpp compiles the same
 // functions with g++ so that the CPU suite checks them, byte for byte, against the stock decoders (OpenCV's libpng /

@@ -1,6 +1,6 @@
 """GPU decoding of capture files: the readers in front of the frame loop.
 
-The reference reads every frame with o3d.io.read_image (/root/reference/3d_model/reconstruct_rgbd.py:90-91) -- libjpeg /
+The reference reads every frame with o3d.io.read_image (/root/reference/3d_model/reconstruct_rgbd.py:88-89) -- libjpeg /
 libpng on one core.  FrameDecoder hands a chunk of files (paths, or bytes already in memory) to
 `otslam_decoder_decode_files` / `otslam_decoder_decode`: host threads only read and frame the files, the compressed bytes
 cross PCIe, and inflate / PNG filters / Huffman / IDCT / upsampling / colour conversion run on the GPU into frame slots
