@@ -212,3 +212,71 @@ def test_colour_jpeg_second_encoder_and_second_decoder(model):
                 ref = cv2.imdecode(np.frombuffer(b, np.uint8), cv2.IMREAD_UNCHANGED)[..., ::-1]
                 pil = np.asarray(Image.open(io.BytesIO(b)).convert("RGB"))
                 assert st == 0 and (o == ref).all() and (o == pil).all(), (H, W, sub, q, opt)
+
+
+def _png_bytes(img, filters, level=6):
+    """A PNG written here: scan line r filtered with filters[r] (PNG spec 9.2), zlib level `level`, one IDAT per 1000 bytes."""
+    import struct
+    import zlib
+    if img.dtype == np.uint16:
+        raw, ctype, depth, bpp = img.astype(">u2").view(np.uint8).reshape(img.shape[0], -1), 0, 16, 2
+    else:
+        raw, ctype, depth, bpp = img.reshape(img.shape[0], -1), (2 if img.shape[2] == 3 else 6), 8, img.shape[2]
+    H, rb = raw.shape
+    lines = []
+    prev = np.zeros(rb, np.int32)
+    for r in range(H):
+        cur = raw[r].astype(np.int32)
+        a = np.concatenate([np.zeros(bpp, np.int32), cur[:-bpp]])
+        b = prev
+        c = np.concatenate([np.zeros(bpp, np.int32), prev[:-bpp]])
+        ft = int(filters[r])
+        if ft == 0:
+            pred = 0
+        elif ft == 1:
+            pred = a
+        elif ft == 2:
+            pred = b
+        elif ft == 3:
+            pred = (a + b) >> 1
+        else:
+            p = a + b - c
+            pa, pb, pc = np.abs(p - a), np.abs(p - b), np.abs(p - c)
+            pred = np.where((pa <= pb) & (pa <= pc), a, np.where(pb <= pc, b, c))
+        lines.append(bytes([ft]) + ((cur - pred) & 255).astype(np.uint8).tobytes())
+        prev = cur
+    z = zlib.compress(b"".join(lines), level)
+
+    def chunk(t, d):
+        return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xFFFFFFFF)
+    out = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", img.shape[1], H, depth, ctype, 0, 0, 0))
+    for i in range(0, len(z), 1000):
+        out += chunk(b"IDAT", z[i:i + 1000])
+    return out + chunk(b"IEND", b"")
+
+
+def test_png_every_filter_in_every_position(model):
+    """Scan lines filtered with random filter types (first line included: Up / Average / Paeth against an all-zero line
+    above), long runs of Paeth (bands that must wait), zlib levels 0 / 1 / 9: the band-parallel reconstruction equals
+    libpng's for every band height and team size."""
+    rng = np.random.default_rng(7)
+    cases = [(rng.integers(0, 65536, (41, 29)).astype(np.uint16), rng.integers(0, 5, 41)),
+             (rng.integers(0, 256, (37, 23, 3)).astype(np.uint8), rng.integers(0, 5, 37)),
+             (rng.integers(0, 256, (19, 31, 4)).astype(np.uint8), np.full(19, 4)),                 # all Paeth: one band does it all
+             ((np.arange(64 * 48).reshape(48, 64) * 7 % 65536).astype(np.uint16), np.array([4, 3, 2] + [1, 0, 2, 3, 4] * 9))]
+    for img, filters in cases:
+        H, W = img.shape[:2]
+        for level in (0, 1, 9):
+            b = _png_bytes(img, filters, level)
+            ref = cv2.imdecode(np.frombuffer(b, np.uint8), cv2.IMREAD_UNCHANGED)
+            want = img if img.ndim == 2 else img[..., :3]
+            assert ref is not None and (ref if img.ndim == 2 else ref[..., :3][..., ::-1]).shape == want.shape
+            assert ((ref if img.ndim == 2 else ref[..., :3][..., ::-1]) == want).all()                 # libpng accepts the file
+            for band, team in ((1, 1), (3, 2), (4, 4), (1000, 3)):
+                st, o = dec_png(model, b, H, W, band, team=team)
+                assert st == 0 and (o == want).all(), (img.shape, level, band, team)
+    # a filter byte > 4 is an error (libpng: "bad adaptive filter value")
+    img, filters = cases[0]
+    bad = filters.copy()
+    bad[5] = 7
+    assert dec_png(model, _png_bytes(img, bad), 41, 29)[0] == 2
