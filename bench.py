@@ -421,7 +421,9 @@ def files_e2e(a, seq, n_files=768):
         done, dt, passes = timed_pass()
         chunks = list(pipeline.last_decode_profile)
         keys = ("inflate_ms", "png_filter_emit_ms", "jpeg_huffman_ms", "jpeg_idct_ms", "jpeg_color_ms")
-        out = {"frames": done, "frames_per_s": done / dt, "pass_ms": passes, "decode": "gpu", "identical_volume": vol._vol.stats() == ref,
+        failed = pipeline.gpu_decode_selfcheck["failed"]
+        out = {"frames": done, "frames_per_s": done / dt, "pass_ms": passes, "decode": "gpu" if not failed else "host (GPU self-check failed: %s)" % failed,
+               "identical_volume": vol._vol.stats() == ref,
                "chunks_in_preparation": pipeline.DECODE_AHEAD,
                "host_threads": pipeline._decode_workers(),
                "decoder_device_ms_per_chunk": {k: float(np.mean([c[k] for c in chunks])) for k in keys} if chunks else None,

@@ -233,6 +233,31 @@ import atexit                                                     # noqa: E402
 atexit.register(release_decoders)                                 # before the CUDA runtime is torn down
 
 
+class GpuDecodeSelfCheckFailed(RuntimeError):
+    pass
+
+
+gpu_decode_selfcheck = {"done": False, "failed": None}    # once per process: see _selfcheck_first_frame
+
+
+def _selfcheck_first_frame(dec, chunk, cstat, dstat):
+    """Once per process, the first frame pair the GPU decoders produced is downloaded and compared with the stock decoders'
+    output for the same two files (7 ms).  The decoders are bit-exact by construction and by test; this is the production
+    guard for the case nobody tested (a driver / hardware oddity): a mismatch never reaches a volume -- the loop raises
+    GpuDecodeSelfCheckFailed before anything is integrated and integrate_files re-runs on the host decoders, loudly."""
+    import cv2
+    for k in range(len(chunk)):
+        if cstat[k] == 0 and dstat[k] == 0:
+            d, c = dec.fetch(k, 1)
+            cc, dd = cv2.imread(chunk[k][0], cv2.IMREAD_UNCHANGED), cv2.imread(chunk[k][1], cv2.IMREAD_UNCHANGED)
+            if cc is None or dd is None or cc.ndim != 3:
+                continue                                          # the stock decoder disagrees about the KIND of file: not this check's business
+            ref = cv2.cvtColor(cc, cv2.COLOR_BGRA2RGB if cc.shape[2] == 4 else cv2.COLOR_BGR2RGB)
+            if dd.shape != d[0].shape or ref.shape != c[0].shape or not (dd == d[0]).all() or not (ref == c[0]).all():
+                raise GpuDecodeSelfCheckFailed(f"GPU-decoded frame differs from the stock decoders: {chunk[k][0]}, {chunk[k][1]}")
+            return
+
+
 def _integrate_files_gpu(volume, triples, intrinsics, T_fix, depth_scale, depth_trunc, skip_errors, progress, on_error):
     """integrate_files with the decoders on the GPU (decoder.py): a chunk's files are read by the library's host threads,
     the compressed bytes are uploaded and decoded in HBM, and the decoded slots go straight into the volume.  DECODE_AHEAD
@@ -279,6 +304,9 @@ def _integrate_files_gpu(volume, triples, intrinsics, T_fix, depth_scale, depth_
                 dec, chunk = decs[ci % len(decs)], chunks[ci]
                 exts = pool.submit(extrinsics, chunk)                                     # while the call below decodes
                 cstat, dstat = dec.decode_files([t[0] for t in chunk], [t[1] for t in chunk])
+                if ci == 0 and not gpu_decode_selfcheck["done"]:         # chunk 0: nothing has been integrated yet
+                    _selfcheck_first_frame(dec, chunk, cstat, dstat)
+                    gpu_decode_selfcheck["done"] = True
                 prof = dec.profile()
                 prof["frames"], prof["passed_on"] = len(chunk), int(np.count_nonzero(cstat | dstat))
                 last_decode_profile.append(prof)
@@ -334,8 +362,13 @@ def integrate_files(volume, triples, intrinsics, T_fix, depth_scale=1000.0, dept
     chunks = [triples[c0:c0 + CHUNK_FRAMES] for c0 in range(0, n, CHUNK_FRAMES)]
     if not chunks:
         return 0
-    if gpu_decode_enabled() and not sidecar_enabled() and isinstance(getattr(volume, "_vol", None), TSDFVolume):
-        return _integrate_files_gpu(volume, triples, intrinsics, T_fix, depth_scale, depth_trunc, skip_errors, progress, on_error)
+    if gpu_decode_enabled() and not sidecar_enabled() and isinstance(getattr(volume, "_vol", None), TSDFVolume) \
+            and gpu_decode_selfcheck["failed"] is None:
+        try:
+            return _integrate_files_gpu(volume, triples, intrinsics, T_fix, depth_scale, depth_trunc, skip_errors, progress, on_error)
+        except GpuDecodeSelfCheckFailed as err:                       # raised before any frame reached the volume
+            gpu_decode_selfcheck["failed"] = str(err)
+            sys.stderr.write(f"[otslam_b200] {err}; GPU decoding is OFF for this process (host decoders take over)\n")
     staging = _Staging.acquire(min(CHUNK_FRAMES, n), intrinsics.height, intrinsics.width, 2 if len(chunks) > 1 else 1)
     try:
         with ThreadPoolExecutor(max_workers=_decode_workers()) as pool:

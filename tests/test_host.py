@@ -391,6 +391,7 @@ def test_gpu_decode_file_loop_orchestration(tmp_path, monkeypatch):
     synth.write_capture_tree(seq, base)
     monkeypatch.setattr(pipeline, "CHUNK_FRAMES", 4)
     monkeypatch.setattr(pipeline, "DECODE_AHEAD", 2)
+    monkeypatch.setattr(pipeline, "gpu_decode_selfcheck", {"done": True, "failed": None})     # its own test below
 
     def triple(i, ok=True):
         return (os.path.join(base, "color", f"Object_0_{i}.jpg"),
@@ -474,3 +475,72 @@ def test_gpu_decode_file_loop_orchestration(tmp_path, monkeypatch):
         pipeline._integrate_files_gpu(Vol, triples, intr, synth.T_FIX, 1000.0, 3.0, False, None, None)
     pipeline._decoder_pool.pop(("fake", 3), None)
     assert [labels for _, labels, _ in state["log"]] == [[1, 2, 3, 4]]
+
+
+def test_gpu_decode_selfcheck_guards_the_first_frame(tmp_path, monkeypatch):
+    """Once per process the first GPU-decoded frame pair is compared with the stock decoders'.  Equal: the loop goes on and
+    never checks again.  Different: GpuDecodeSelfCheckFailed before anything is integrated, and integrate_files re-runs the
+    whole list on the host decoders (every frame integrated exactly once) and keeps GPU decoding off for the process."""
+    import threading
+    import cv2
+    from otslam_b200.volume import TSDFVolume
+    intr = o3d.camera.PinholeCameraIntrinsic(64, 48, 56.0, 56.0, 32.5, 24.5)
+    seq = synth.make_sequence("table", 6, intr=(64, 48, 56.0, 56.0, 32.5, 24.5))
+    base = str(tmp_path / "scan")
+    synth.write_capture_tree(seq, base)
+    triples = [(os.path.join(base, "color", f"Object_0_{i}.jpg"), os.path.join(base, "depth", f"Object_0_{i}.png"),
+                os.path.join(base, "poses", f"Object_0_{i}.txt"), i) for i in range(1, 7)]
+    monkeypatch.setattr(pipeline, "CHUNK_FRAMES", 4)
+    log = []
+
+    class FakeDecoder:
+        wrong = False
+
+        def decode_files(self, cps, dps):
+            self.cps, self.dps = cps, dps
+            return np.zeros(len(cps), np.int32), np.zeros(len(cps), np.int32)
+
+        def fetch(self, first, count):
+            d = cv2.imread(self.dps[first], cv2.IMREAD_UNCHANGED)[None].copy()
+            c = cv2.imread(self.cps[first], cv2.IMREAD_UNCHANGED)[..., ::-1][None].copy()
+            if FakeDecoder.wrong:
+                c[0, 3, 5, 1] ^= 1                              # one bit of one colour sample
+            return d, c
+
+        def profile(self):
+            return {"compressed_bytes": 0}
+
+        def integrate(self, vol, slots, k, exts, s, t):
+            log.append(("gpu", len(slots)))
+
+        def close(self):
+            pass
+
+    def acquire(count, h, w, frames, device):
+        pipeline._decoder_lock = pipeline._decoder_lock or threading.Lock()
+        return [FakeDecoder() for _ in range(count)], ("fake2", count)
+
+    monkeypatch.setattr(pipeline, "_acquire_decoders", acquire)
+
+    class Vol:
+        _vol = object.__new__(TSDFVolume)                       # passes the isinstance test; never touched by the fakes
+        _vol.device = 0
+
+        def integrate_sequence(self, d, c, i, e, s, t):
+            log.append(("host", len(e)))
+
+    monkeypatch.setenv("OTSLAM_GPU_DECODE", "1")
+    monkeypatch.delenv("OTSLAM_SIDECAR", raising=False)
+    state = {"done": False, "failed": None}
+    monkeypatch.setattr(pipeline, "gpu_decode_selfcheck", state)
+    assert pipeline.integrate_files(Vol(), triples, intr, synth.T_FIX) == 6
+    assert log == [("gpu", 4), ("gpu", 2)] and state == {"done": True, "failed": None}
+    # a decoder that gets one bit wrong
+    log.clear()
+    state.update(done=False, failed=None)
+    FakeDecoder.wrong = True
+    assert pipeline.integrate_files(Vol(), triples, intr, synth.T_FIX) == 6
+    assert log == [("host", 4), ("host", 2)] and state["failed"] and "differs from the stock decoders" in state["failed"]
+    log.clear()
+    assert pipeline.integrate_files(Vol(), triples, intr, synth.T_FIX) == 6 and log == [("host", 4), ("host", 2)]   # stays off
+    pipeline._decoder_pool.pop(("fake2", 2), None)
