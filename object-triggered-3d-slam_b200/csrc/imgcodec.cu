@@ -519,8 +519,9 @@ int decode_sources(otslam_decoder* d, int n, const Source* color, const Source* 
 extern "C" {
 
 int otslam_decoder_create(int device, int height, int width, int max_frames, otslam_decoder** out) {
-    if (!out || height <= 0 || width <= 0 || max_frames <= 0 || (int64_t)height * width > (1ll << 28))
-        return set_error(OTSLAM_ERR_INVALID, "decoder_create: bad arguments");
+    // (2 x max_frames is a grid dimension of the per-pixel kernels; an image's scan lines must stay below 2^31 bytes)
+    if (!out || height <= 0 || width <= 0 || max_frames <= 0 || max_frames > 16384 || (int64_t)height * width > (1ll << 28))
+        return set_error(OTSLAM_ERR_INVALID, "decoder_create: bad arguments (max_frames <= 16384, height x width <= 2^28)");
     *out = nullptr;
     OT_TRY(use_device(device));
     auto* d = new otslam_decoder();
