@@ -280,3 +280,17 @@ def test_png_every_filter_in_every_position(model):
     bad = filters.copy()
     bad[5] = 7
     assert dec_png(model, _png_bytes(img, bad), 41, 29)[0] == 2
+
+
+def test_hd_frame_pair_equals_stock_decoders(model):
+    """configs[3] geometry: one 1280x720 frame pair of the large room as cv::imwrite stores it."""
+    from otslam_b200 import synth
+    seq = synth.make_sequence("room", 40, intr=synth.HD_INTRINSICS, subsample=(0, 20))
+    dep, rgb = seq.numpy()
+    for k in range(len(dep)):
+        ok, e = cv2.imencode(".jpg", rgb[k][..., ::-1])
+        st, o = dec_jpg(model, e.tobytes(), 720, 1280)
+        assert st == 0 and (o == cv2.imdecode(e, cv2.IMREAD_UNCHANGED)[..., ::-1]).all()
+        ok, e = cv2.imencode(".png", dep[k])
+        st, o = dec_png(model, e.tobytes(), 720, 1280, 4, team=4)
+        assert st == 0 and (o == dep[k]).all()
