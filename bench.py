@@ -331,6 +331,60 @@ def post_stage(a, vol, n_blocks, peak):
     return out
 
 
+def config3_stage(a, device, frames_per_object=150, repeats=3):
+    """BASELINE configs[2] (multi_reconstruct_rgbd_filter.py:139-145): four objects (table, chair, cone, cardboard), each its
+    own volume in the reference, one after the other.  Frames resident in HBM, 640x480, the bench's voxel size.
+    sequential = four volumes integrated one after the other (the reference's structure on the GPU); arena = ONE multi-object
+    arena (object id in the block key) fed with the four objects' frames interleaved as pipeline.interleave_plan orders them:
+    one work list and one integration launch per 32-frame batch over the union of the objects' blocks.  A single small
+    object's batch touches a few hundred blocks and cannot fill 148 SMs; the union can.  Wall clock around the synchronous
+    calls, best of `repeats`; every object's statistics must be equal both ways."""
+    import torch
+    from otslam_b200 import pipeline, synth
+    from otslam_b200.volume import ArenaView, TSDFVolume
+    scenes = ("table", "chair", "cone", "cardboard")
+    seqs = [synth.make_sequence(s, frames_per_object, device=device) for s in scenes]
+    counts = [len(s) for s in seqs]
+    order = pipeline.interleave_plan(counts)
+    base = np.cumsum([0] + counts[:-1])
+    idx = torch.tensor([int(base[o]) + k for o, k in order], device=device)
+    # (indexing through an int16 view: advanced indexing of uint16 tensors is not available on every torch build)
+    depth = torch.cat([s.depth for s in seqs]).view(torch.int16)[idx].view(seqs[0].depth.dtype).contiguous()
+    rgb = torch.cat([s.rgb for s in seqs])[idx].contiguous()
+    ext = np.concatenate([s.extrinsic for s in seqs])[idx.cpu().numpy()]
+    ids = np.array([o for o, _ in order], np.int32)
+    dev_index = torch.device(device).index or 0
+    vols = [TSDFVolume(a.voxel, 4 * a.voxel, device=dev_index) for _ in scenes]
+    arena = TSDFVolume(a.voxel, 4 * a.voxel, device=dev_index)
+    arena.set_objects(len(scenes))
+    try:
+        t_seq = t_arena = 1e30
+        for _ in range(repeats + 1):                              # first pass warms pools and staging
+            for v in vols:
+                v.reset()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for v, s in zip(vols, seqs):
+                v.integrate_batch(s.depth.contiguous(), s.rgb.contiguous(), s.fxfycxcy, s.extrinsic)
+            t_seq = min(t_seq, time.perf_counter() - t0)
+            arena.reset()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            arena.integrate_batch(depth, rgb, seqs[0].fxfycxcy, ext, object_ids=ids)
+            t_arena = min(t_arena, time.perf_counter() - t0)
+        per_obj = [v.stats() for v in vols]
+        same = all(ArenaView(arena, o).stats() == per_obj[o] for o in range(len(scenes)))
+        n = sum(counts)
+        return {"objects": list(scenes), "frames": n, "frames_per_object": frames_per_object, "voxel": a.voxel,
+                "sequential_frames_per_s": n / t_seq, "arena_frames_per_s": n / t_arena, "arena_speedup": t_seq / t_arena,
+                "identical_per_object": bool(same), "blocks_per_object": [st["n_blocks"] for st in per_obj],
+                "note": "frames resident in HBM; wall clock of the synchronous C-ABI calls, best of %d" % repeats}
+    finally:
+        for v in vols:
+            v.close()
+        arena.close()
+
+
 def hybrid_merge_stage(peak, n_obj=20, per_obj=1_000_000, map_px=2000):
     """BASELINE.json configs[4]: fusion/hybrid_map.py -- 2-D occupancy grid -> Z = 0 points (reference :45-55, a Python
     per-pixel loop) and the paint + concatenate + PLY-record packing of `n_obj` object clouds of `per_obj` points
@@ -765,6 +819,10 @@ def run_ours(a):
                 post["hybrid_map_config5"] = hybrid_merge_stage(peak)
             except Exception as e:  # noqa: BLE001
                 post["hybrid_map_config5"] = {"error": repr(e)}
+            try:
+                post["config3_four_objects"] = config3_stage(a, f"cuda:{local}")
+            except Exception as e:  # noqa: BLE001 -- informational
+                post["config3_four_objects"] = {"error": repr(e)}
             try:
                 post["files_e2e"] = files_e2e(a, seq)
             except Exception as e:  # noqa: BLE001 -- informational; never let it take the bench line down
