@@ -339,6 +339,7 @@ def config3_stage(a, device, frames_per_object=150, repeats=3):
     one work list and one integration launch per 32-frame batch over the union of the objects' blocks.  A single small
     object's batch touches a few hundred blocks and cannot fill 148 SMs; the union can.  Wall clock around the synchronous
     calls, best of `repeats`; every object's statistics must be equal both ways."""
+    import numpy as np
     import torch
     from otslam_b200 import pipeline, synth
     from otslam_b200.volume import ArenaView, TSDFVolume
